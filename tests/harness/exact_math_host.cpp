@@ -1,0 +1,22 @@
+// Host build of the product's exact-arithmetic header (vi_depth_completion_b200/csrc/exact_math.cuh)
+// so the CPU test-suite can sweep it against libm / torch without a GPU.
+#include "../../vi_depth_completion_b200/csrc/exact_math.cuh"
+#include <stddef.h>
+extern "C" {
+void host_glibc_atan2f(const float* y, const float* x, size_t n, float* out) {
+    for (size_t i = 0; i < n; ++i) out[i] = vidc::glibc_atan2f(y[i], x[i]);
+}
+void host_mkl_cosf_ha(const float* x, size_t n, float* out) {
+    for (size_t i = 0; i < n; ++i) out[i] = vidc::mkl_cosf_ha(x[i]);
+}
+// exhaustive self-check against the C library: all y-bit-patterns in [ylo, yhi) step ystep, for a fixed x
+size_t host_atan2f_sweep_vs_libm(uint32_t ylo, uint32_t yhi, uint32_t ystep, float x) {
+    size_t bad = 0;
+    for (uint64_t b = ylo; b < yhi; b += ystep) {
+        const float y = vidc::u2f((uint32_t)b);
+        const float a = vidc::glibc_atan2f(y, x), r = atan2f(y, x);
+        if (vidc::f2u(a) != vidc::f2u(r) && !(a != a && r != r)) ++bad;
+    }
+    return bad;
+}
+}
