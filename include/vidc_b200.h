@@ -1,0 +1,190 @@
+/*
+ * vidc_b200.h -- C ABI of the B200-native gravity warp / unwarp path.
+ *
+ * This is the drop-in boundary: a plain C interface (pointers, sizes, a CUDA stream handle;
+ * no torch or C++ types) that replaces, call for call, the PyTorch implementation in
+ * MARSLab-UMN/vi_depth_completion:
+ *
+ *     networks/warping_2dof_alignment.py   class Warping2DOFAlignment          (:5-310)
+ *     networks/surface_normal.py           mask / pyramid masks / renormalise  (:150-156, :170)
+ *     normal_utils.py                      masked angular statistics           (:7-34)
+ *
+ * Each entry point cites the reference lines it replaces.  The Python mirror of the reference
+ * class (vi_depth_completion_b200/warping_2dof_alignment.py) binds these symbols with ctypes;
+ * INTEGRATION.md shows the binding a reference maintainer adds.
+ *
+ * Conventions
+ *   - All tensors are IEEE fp32 (the reference casts with .type(torch.float), :115-116).
+ *   - Pointers named d_* are DEVICE pointers on the CUDA device that is current when the call
+ *     is made; pointers named h_* are HOST pointers.  Nothing is ever written through an input.
+ *   - Images are described by a vidc_image: logical NCHW shape plus element strides, so both
+ *     contiguous NCHW and channels-last (NHWC) storage are consumed / produced without a copy.
+ *   - Every device entry point is asynchronous: it enqueues kernels on `stream` (a cudaStream_t
+ *     passed as void*; NULL = the legacy default stream) and returns without synchronising.
+ *   - Return value: VIDC_OK (0) or a negative vidc_status.  vidc_last_error() gives the message
+ *     for the calling thread.  No entry point aborts the process.
+ *   - Results are bit-identical to the reference executed on CPU with torch 2.11 (the pinned
+ *     oracle) -- parameters, sampling grids, warped images, masks and rotated /
+ *     renormalised normals.
+ */
+#ifndef VIDC_B200_H
+#define VIDC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VIDC_ABI_VERSION 1
+
+typedef enum vidc_status {
+    VIDC_OK = 0,
+    VIDC_ERR_INVALID_ARGUMENT = -1, /* shape / stride / null-pointer / enum problems (torch RuntimeError) */
+    VIDC_ERR_BATCH_MISMATCH = -2,   /* x.shape[0] != I_g.shape[0]  (reference: AssertionError, :123,:224) */
+    VIDC_ERR_CUDA = -3,             /* a CUDA runtime call failed; message carries cudaGetErrorString */
+    VIDC_ERR_NO_DEVICE = -4         /* no sm_100 device is current */
+} vidc_status;
+
+typedef enum vidc_interp {
+    VIDC_BILINEAR = 0, /* interp_mode='bilinear' (:108) */
+    VIDC_NEAREST = 1   /* interp_mode='nearest'             */
+} vidc_interp;
+
+/* Camera constants of Warping2DOFAlignment.__init__ (:6-24).  Plain host struct. */
+typedef struct vidc_camera {
+    int32_t W, H;        /* ceil(2cx), ceil(2cy)                                  :13-14 */
+    float K[9];          /* intrinsics, fp64 -> fp32                              :15,:19 */
+    float Kinv[9];       /* np.linalg.inv(K) in fp64 -> fp32                      :16,:20 */
+    float cx, cy;        /* principal point rounded once to fp32                  :149-150 */
+    float inv_half_w;    /* float(1. / (W / 2))                                   :149 */
+    float inv_half_h;    /* float(1. / (H / 2))                                   :150 */
+    float fx, fy;
+} vidc_camera;
+
+/* Per-frame parameters produced by _build_homography (:35-58) and the bounding-box / scale
+   block that the reference repeats in every method (:125-140, :168-194, :226-240). 48 floats. */
+typedef struct vidc_frame_params {
+    float H[9];      /* Cg_H_C      = K R K^-1                    :55 */
+    float R[9];      /* Cg_R_C                                    :53-54 */
+    float Hinv[9];   /* Cg_H_C_inv  = K R^T K^-1                  :56-57 */
+    float px_min, py_min;  /* :128,:130 */
+    float kw, kh;          /* :135-140 */
+    float ikw, ikh;        /* "1./kw", "1./kh"  :142-143 */
+    float w_max, h_max;    /* :132-133 */
+    float reserved[13];
+} vidc_frame_params;
+
+/* Logical (N, C, H, W) image batch with element strides. */
+typedef struct vidc_image {
+    float *data;                 /* device pointer */
+    int32_t n, c, h, w;
+    int64_t sn, sc, sh, sw;      /* strides in elements */
+} vidc_image;
+
+/* ------------------------------------------------------------------------------------------ */
+
+/* ABI version of the loaded library. */
+int vidc_abi_version(void);
+
+/* Message of the last failing call on this thread ("" if none). */
+const char *vidc_last_error(void);
+
+/* Replaces Warping2DOFAlignment.__init__ (:6-24).  Host only. */
+int vidc_camera_init(double fx, double fy, double cx, double cy, vidc_camera *cam);
+
+/* Replaces _build_homography (:35-58) plus the per-frame bbox / scale block (:125-140).
+   d_Ig, d_Ia: (B,3) contiguous.  d_params: B entries. One thread per frame, no host sync. */
+int vidc_frame_params_compute(const vidc_camera *cam, const float *d_Ig, const float *d_Ia, int32_t B,
+                              vidc_frame_params *d_params, void *stream);
+
+/* _build_homography's return tuple (:58): scatters params into three contiguous (B,3,3) tensors.
+   Any of d_H, d_R, d_Hinv may be NULL. */
+int vidc_build_homography(const vidc_camera *cam, const float *d_Ig, const float *d_Ia, int32_t B,
+                          float *d_H, float *d_R, float *d_Hinv, void *stream);
+
+/* Replaces warp_with_gravity_center_aligned (:108-156): fused params + grid + grid_sample.
+   x: (B,C,Hin,Win) any strides; y: (B,C,cam.H,cam.W).  d_H_out (B,3,3) may be NULL.
+   d_params_ws: caller-owned scratch of B vidc_frame_params (may alias across calls). */
+int vidc_warp_forward(const vidc_camera *cam, const vidc_image *x, const float *d_Ig, const float *d_Ia,
+                      int32_t B_gravity, vidc_interp mode, vidc_frame_params *d_params_ws,
+                      float *d_H_out, const vidc_image *y, void *stream);
+
+/* Fused single-pass forward warp of RGB (3ch, bilinear) AND sparse depth (1ch, depth_mode),
+   plus the validity mask of surface_normal.py:151 and per-frame coverage counts.
+   rgb_out/depth_out as in vidc_warp_forward.  Optional outputs (NULL to skip):
+     d_mask_u8   (B, cam.H, cam.W) uint8, 1 where (R+G)+B > float(1e-2)
+     d_coverage  (B) uint32, number of mask pixels per frame (warp-shuffle + one atomic per CTA;
+                 zeroed by the call)
+   depth may be NULL (RGB only). */
+int vidc_warp_rgbd(const vidc_camera *cam, const vidc_image *rgb, const vidc_image *depth,
+                   const float *d_Ig, const float *d_Ia, int32_t B_gravity, vidc_interp depth_mode,
+                   vidc_frame_params *d_params_ws, float *d_H_out,
+                   const vidc_image *rgb_out, const vidc_image *depth_out,
+                   uint8_t *d_mask_u8, uint32_t *d_coverage, void *stream);
+
+/* Replaces inverse_warp_normal_image_with_gravity_center_aligned (:216-255) and, when
+   `normalize` != 0, also the caller's F.normalize(z, dim=1) (surface_normal.py:170) in the same
+   pass: gather + R^T rotation (+ renormalise).  x, z: (B,3,cam.H,cam.W).
+   d_valid_u8 (B,H,W), optional: 1 where the sample footprint touched the canvas. */
+int vidc_unwarp_normals(const vidc_camera *cam, const vidc_image *x, const float *d_Ig, const float *d_Ia,
+                        int32_t B_gravity, int32_t normalize, vidc_frame_params *d_params_ws,
+                        float *d_H_out, const vidc_image *z, uint8_t *d_valid_u8, void *stream);
+
+/* Replaces image_sampler_forward_inverse (:158-214) including the aspect guard (:178-187).
+   d_Rt (B,3,3), d_grid / d_inv_grid (B,H,W,2) contiguous; any may be NULL. */
+int vidc_sampler_forward_inverse(const vidc_camera *cam, const float *d_Ig, const float *d_Ia, int32_t B,
+                                 vidc_frame_params *d_params_ws, float *d_Rt, float *d_grid,
+                                 float *d_inv_grid, void *stream);
+
+/* Replaces warp_normal_image_with_gravity_center_aligned (:258-290) as evidently intended
+   (the reference method raises at :259): forward warp of a 3-channel normal image followed by
+   the per-pixel rotation z = R y. */
+int vidc_warp_normals_forward(const vidc_camera *cam, const vidc_image *x, const float *d_Ig, const float *d_Ia,
+                              int32_t B_gravity, vidc_interp mode, vidc_frame_params *d_params_ws,
+                              float *d_H_out, const vidc_image *z, void *stream);
+
+/* Replaces warp_with_homography (:292-310): explicit homographies, NON-uniform kw/kh (:299-300).
+   d_Hm: (B,3,3) device.  The inverse is taken per frame in fp64 (np.linalg.inv, :301). */
+int vidc_warp_with_homography(const vidc_camera *cam, const vidc_image *x, const float *d_Hm, int32_t B_h,
+                              vidc_frame_params *d_params_ws, const vidc_image *y, void *stream);
+
+/* surface_normal.py:151: mask = (x1[:,0]+x1[:,1])+x1[:,2] > float(1e-2), as uint8 and/or float. */
+int vidc_validity_mask(const vidc_image *x1, uint8_t *d_mask_u8, float *d_mask_f32,
+                       uint32_t *d_coverage, void *stream);
+
+/* surface_normal.py:153-156: F.interpolate(mask, size, 'nearest') for float masks (B,1,Hin,Win). */
+int vidc_mask_nearest(const float *d_mask, int32_t B, int32_t Hin, int32_t Win,
+                      int32_t Hout, int32_t Wout, float *d_out, void *stream);
+
+/* surface_normal.py:170: F.normalize(z, dim=1) for 3-channel images. */
+int vidc_normalize3(const vidc_image *z, const vidc_image *out, void *stream);
+
+/* normal_utils.py:20-34 (and :7-17): one pass producing, in d_out[4] (fp64, zeroed by the call):
+     [0] sum(angle_deg * mask)   [1] sum(mask)   [2] sum |n*mask - gt*mask|   [3] sum cos_sim
+   pred: (B,>=3,H,W) (first three channels used), gt: (B,3,H,W), mask: (B,1,H,W) float. */
+int vidc_normal_stats(const vidc_image *gt, const vidc_image *pred, const vidc_image *mask,
+                      int32_t normalize_prediction, double *d_out, void *stream);
+
+/* ---- host-buffer end-to-end entry point (bench.py `e2e`, simple embedders) ------------------
+   One frame batch through the whole path with HOST buffers: H2D of rgb/depth/normals/gravity,
+   warp_rgbd, unwarp_normals(normalize=1), D2H of the four outputs.  Buffers are contiguous NCHW.
+   Any of the output pointers may be NULL (not copied back).  Pinned host memory makes the copies
+   asynchronous; the call synchronises `stream` before returning.  Device scratch is cached per
+   (device, size) inside the library and released by vidc_release_workspace(). */
+int vidc_warp_unwarp_host(const vidc_camera *cam, int32_t B,
+                          const float *h_rgb, const float *h_depth, const float *h_normals,
+                          const float *h_Ig, const float *h_Ia,
+                          float *h_rgb_w, float *h_depth_w, uint8_t *h_mask, float *h_normals_cam,
+                          void *stream);
+int vidc_release_workspace(void);
+
+/* Number of kernel launches issued by this library since load (all threads). For bench.py's
+   gpu_launches accounting. */
+uint64_t vidc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIDC_B200_H */

@@ -1,0 +1,193 @@
+"""Parity of the CUDA path (through the C ABI, via the drop-in class) against the CPU oracle.
+
+Bar (BASELINE.json north_star): masks bit-exact, warped RGB / depth within 1e-4 abs, normals within
+0.01 degrees.  The kernels restate the reference's fp32 roundings, so these tests additionally assert
+the stronger property that holds today: ZERO differing bits in every output.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests import common as C
+
+pytestmark = pytest.mark.gpu
+
+RGBD_ATOL = 1e-4       # north_star: warped RGB and depth within 1e-4 absolute in fp32
+NORMAL_ATOL_DEG = 0.01  # north_star: normals within 0.01 degrees
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _mk(cam_name, dev):
+    from vi_depth_completion_b200.warping_2dof_alignment import Warping2DOFAlignment
+    from oracle import oracle as O
+    fx, fy, cx, cy = C.CAMERAS[cam_name]
+    return Warping2DOFAlignment(fx=fx, fy=fy, cx=cx, cy=cy), O.Oracle(fx, fy, cx, cy)
+
+
+def _check_params(w, o, I_g, I_a, dev):
+    H, R, Hi = w._build_homography(_t(I_g, dev), _t(I_a, dev))
+    oH, oR, oHi = o.build_homography(I_g, I_a)
+    assert C.count_bit_mismatches(R.cpu().numpy(), oR) == 0
+    assert C.count_bit_mismatches(H.cpu().numpy(), oH) == 0
+    assert C.count_bit_mismatches(Hi.cpu().numpy(), oHi) == 0
+    prm = w.frame_params(_t(I_g, dev), _t(I_a, dev)).cpu().numpy()
+    sc = o.frame_scale(oH)
+    assert C.count_bit_mismatches(prm[:, 27:35], sc) == 0
+
+
+@pytest.mark.parametrize("cam_name,B,roll,pitch", [("S1", 512, 30, 30), ("S2", 512, 30, 30), ("S3", 512, 75, 40),
+                                                    ("default", 256, 89, 60), ("tiny", 256, 45, 45)])
+def test_frame_params_bit_exact(cuda_device, oracle_mod, cam_name, B, roll, pitch):
+    w, o = _mk(cam_name, cuda_device)
+    I_g, I_a = C.random_gravity(B, seed=11, roll_deg=roll, pitch_deg=pitch)
+    _check_params(w, o, I_g, I_a, cuda_device)
+
+
+def test_frame_params_edge_cases(cuda_device, oracle_mod):
+    for cam_name in ("S1", "S3"):
+        w, o = _mk(cam_name, cuda_device)
+        I_g, I_a = C.edge_case_gravity()
+        _check_params(w, o, I_g, I_a, cuda_device)
+        I_g, I_a = C.extreme_roll_gravity(64, seed=5)
+        _check_params(w, o, I_g, I_a, cuda_device)
+
+
+def _full_path(cam_name, B, I_g, I_a, dev, seed, sparse_depth=False, depth_mode="bilinear", smooth=False):
+    w, o = _mk(cam_name, dev)
+    Hh, Ww = int(w.H), int(w.W)
+    rgb, depth, normals = C.random_images(B, Hh, Ww, seed, sparse_depth=sparse_depth)
+    if smooth:
+        rgb = C.smooth_images(B, Hh, Ww, seed)
+    g, a = _t(I_g, dev), _t(I_a, dev)
+    # --- reference-shaped calls (the drop-in API) ---
+    H1, y = w.warp_with_gravity_center_aligned(_t(rgb, dev), g, a)
+    H2, yd = w.warp_with_gravity_center_aligned(_t(depth, dev), g, a, interp_mode=depth_mode)
+    H3, z = w.inverse_warp_normal_image_with_gravity_center_aligned(_t(normals, dev), g, a)
+    zn = torch.nn.functional.normalize(z, dim=1)
+    # --- fused entry points ---
+    H4, rgb_w, depth_w, mask = w.warp_rgbd(_t(rgb, dev), _t(depth, dev), g, a, depth_mode=depth_mode)
+    H5, nhat = w.unwarp_normals(_t(normals, dev), g, a)
+    torch.cuda.synchronize()
+    # --- oracle ---
+    oH, oy = o.warp_with_gravity_center_aligned(rgb, I_g, I_a)
+    _, oyd = o.warp_with_gravity_center_aligned(depth, I_g, I_a, interp_mode=depth_mode)
+    _, oz = o.inverse_warp_normal_image_with_gravity_center_aligned(normals, I_g, I_a)
+    from oracle import oracle as O
+    ozn = O.normalize(oz)
+    omask = O.validity_mask(oy)
+
+    y, yd, z, zn = y.cpu().numpy(), yd.cpu().numpy(), z.cpu().numpy(), zn.cpu().numpy()
+    rgb_w, depth_w, mask, nhat = rgb_w.cpu().numpy(), depth_w.cpu().numpy(), mask.cpu().numpy(), nhat.cpu().numpy()
+    for Hx in (H1, H2, H3, H4, H5):
+        assert C.count_bit_mismatches(Hx.cpu().numpy(), oH) == 0
+    # tolerance bar of the north star
+    assert np.nanmax(np.abs(y - oy)) <= RGBD_ATOL
+    assert np.nanmax(np.abs(yd - oyd)) <= RGBD_ATOL
+    err, ok = C.angular_error_deg(nhat, ozn)
+    assert err.size == 0 or err.max() <= NORMAL_ATOL_DEG
+    assert np.array_equal(nhat[:, 0][~ok] == 0, ozn[:, 0][~ok] == 0)
+    assert np.array_equal(mask, omask)                         # masks bit-exact
+    # the stronger property: identical bits everywhere
+    assert C.count_bit_mismatches(y, oy) == 0
+    assert C.count_bit_mismatches(yd, oyd) == 0
+    assert C.count_bit_mismatches(z, oz) == 0
+    assert C.count_bit_mismatches(nhat, ozn) == 0
+    assert C.count_bit_mismatches(rgb_w, oy) == 0
+    assert C.count_bit_mismatches(depth_w, oyd) == 0
+    assert C.count_bit_mismatches(zn, ozn) <= zn.size // 1000   # torch's own normalize on GPU: informational
+    return w, o
+
+
+@pytest.mark.parametrize("cam_name,B,roll,pitch", [("tiny", 16, 45, 45), ("S1", 8, 30, 30), ("S2", 4, 30, 30), ("S3", 4, 75, 40)])
+def test_warp_unwarp_matches_oracle(cuda_device, oracle_mod, cam_name, B, roll, pitch):
+    I_g, I_a = C.random_gravity(B, seed=1234, roll_deg=roll, pitch_deg=pitch)
+    _full_path(cam_name, B, I_g, I_a, cuda_device, seed=1)
+
+
+def test_warp_unwarp_extreme_roll(cuda_device, oracle_mod):
+    I_g, I_a = C.extreme_roll_gravity(7, seed=3)
+    _full_path("S3", 7, I_g, I_a, cuda_device, seed=2)
+
+
+def test_warp_unwarp_edge_cases(cuda_device, oracle_mod):
+    I_g, I_a = C.edge_case_gravity()
+    _full_path("S1", I_g.shape[0], I_g, I_a, cuda_device, seed=4)
+    _full_path("tiny", I_g.shape[0], I_g, I_a, cuda_device, seed=4, smooth=True)
+
+
+def test_sparse_depth_nearest_and_bilinear(cuda_device, oracle_mod):
+    I_g, I_a = C.random_gravity(6, seed=77)
+    _full_path("S1", 6, I_g, I_a, cuda_device, seed=5, sparse_depth=True, depth_mode="nearest")
+    _full_path("S1", 6, I_g, I_a, cuda_device, seed=5, sparse_depth=True, depth_mode="bilinear")
+
+
+def test_sampler_grids_match_oracle(cuda_device, oracle_mod):
+    for cam_name in ("tiny", "S1"):
+        w, o = _mk(cam_name, cuda_device)
+        I_g, I_a = C.edge_case_gravity()
+        Rt, grid, inv = w.image_sampler_forward_inverse(_t(I_g, cuda_device), _t(I_a, cuda_device))
+        oRt, ogrid, oinv = o.image_sampler_forward_inverse(I_g, I_a)
+        assert C.count_bit_mismatches(Rt.cpu().numpy(), oRt) == 0
+        assert C.count_bit_mismatches(grid.cpu().numpy(), ogrid) == 0
+        assert C.count_bit_mismatches(inv.cpu().numpy(), oinv) == 0
+
+
+def test_input_size_differs_from_canvas(cuda_device, oracle_mod):
+    """Forward warp of a 640x480 image into the 320x240 canvas (the demo path resizes; the API allows any size)."""
+    w, o = _mk("S1", cuda_device)
+    I_g, I_a = C.random_gravity(3, seed=9)
+    rgb, _, _ = C.random_images(3, 480, 640, seed=6)
+    _, y = w.warp_with_gravity_center_aligned(_t(rgb, cuda_device), _t(I_g, cuda_device), _t(I_a, cuda_device))
+    _, oy = o.warp_with_gravity_center_aligned(rgb, I_g, I_a)
+    assert C.count_bit_mismatches(y.cpu().numpy(), oy) == 0
+
+
+def test_channels_last_input_no_copy(cuda_device, oracle_mod):
+    w, o = _mk("S1", cuda_device)
+    I_g, I_a = C.random_gravity(4, seed=21)
+    rgb, _, normals = C.random_images(4, int(w.H), int(w.W), seed=8)
+    x = _t(rgb, cuda_device).contiguous(memory_format=torch.channels_last)
+    _, y = w.warp_with_gravity_center_aligned(x, _t(I_g, cuda_device), _t(I_a, cuda_device))
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    _, oy = o.warp_with_gravity_center_aligned(rgb, I_g, I_a)
+    assert C.count_bit_mismatches(y.cpu().numpy(), oy) == 0
+    n = _t(normals, cuda_device).contiguous(memory_format=torch.channels_last)
+    _, z = w.unwarp_normals(n, _t(I_g, cuda_device), _t(I_a, cuda_device), normalize=False)
+    _, oz = o.inverse_warp_normal_image_with_gravity_center_aligned(normals, I_g, I_a)
+    assert C.count_bit_mismatches(z.cpu().numpy(), oz) == 0
+
+
+def test_coverage_counts(cuda_device, oracle_mod):
+    w, o = _mk("S1", cuda_device)
+    I_g, I_a = C.random_gravity(5, seed=31)
+    rgb, depth, _ = C.random_images(5, int(w.H), int(w.W), seed=9)
+    _, rgb_w, _, mask, cov = w.warp_rgbd(_t(rgb, cuda_device), _t(depth, cuda_device), _t(I_g, cuda_device), _t(I_a, cuda_device),
+                                         with_coverage=True)
+    assert np.array_equal(cov.cpu().numpy(), mask.cpu().numpy().reshape(5, -1).sum(1))
+
+
+def test_errors(cuda_device):
+    w, _ = _mk("S1", cuda_device)
+    g = torch.zeros(2, 3, device=cuda_device); g[:, 1] = 1
+    with pytest.raises(AssertionError):                     # reference :123
+        w.warp_with_gravity_center_aligned(torch.zeros(3, 3, 240, 320, device=cuda_device), g, g)
+    with pytest.raises(RuntimeError):
+        w.warp_with_gravity_center_aligned(torch.zeros(2, 3, 240, 320, device=cuda_device, dtype=torch.float64), g, g)
+    with pytest.raises(RuntimeError):
+        w.warp_with_gravity_center_aligned(torch.zeros(2, 3, 240, 320), g, g)          # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        w.inverse_warp_normal_image_with_gravity_center_aligned(torch.zeros(2, 3, 100, 100, device=cuda_device), g, g)
+    x = torch.zeros(2, 3, 240, 320, device=cuda_device, requires_grad=True)
+    _, y = w.warp_with_gravity_center_aligned(x, g, g)
+    with pytest.raises(NotImplementedError):
+        y.sum().backward()
+
+
+def test_empty_batch(cuda_device):
+    w, _ = _mk("S1", cuda_device)
+    g = torch.zeros(0, 3, device=cuda_device)
+    H, y = w.warp_with_gravity_center_aligned(torch.zeros(0, 3, 240, 320, device=cuda_device), g, g)
+    assert y.shape == (0, 3, 240, 320) and H.shape == (0, 3, 3)

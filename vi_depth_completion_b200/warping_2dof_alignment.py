@@ -1,0 +1,308 @@
+"""Drop-in replacement for the reference's networks/warping_2dof_alignment.py.
+
+Same class name, constructor and method signatures / return tuples as
+MARSLab-UMN/vi_depth_completion `Warping2DOFAlignment` (networks/warping_2dof_alignment.py:5-310),
+so networks/surface_normal.py (:70, :148, :169) runs unmodified on top of it.  Every method is a thin
+host-side wrapper: it checks shapes, allocates the outputs with torch (device memory + streams are
+the only things torch is used for) and enqueues the hand-written sm_100a kernels of
+libvidc_b200.so on the current CUDA stream through the C ABI in include/vidc_b200.h.
+
+Differences from the reference that are deliberate:
+  * the device follows the inputs (the reference pins 'cuda:0', :7);
+  * nothing synchronises with the host (the reference reads dozens of device scalars per frame);
+  * any canvas size works (the reference hard-codes 240*320 staging buffers, :121-122);
+  * forward only: tensors that require grad raise NotImplementedError in backward;
+  * there is NO CPU / PyTorch fallback: CPU tensors raise RuntimeError.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import VidcCamera, VidcImage, check, lib
+
+__all__ = ["Warping2DOFAlignment"]
+
+
+def _stream_ptr(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda_f32(t: torch.Tensor, name: str):
+    if not isinstance(t, torch.Tensor):
+        raise RuntimeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (this module has no CPU fallback), got device {t.device}")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name}: expected scalar type Float but found {t.dtype}")
+
+
+def _image(t: torch.Tensor) -> VidcImage:
+    """(N,C,H,W) tensor -> vidc_image with element strides (no copy for NCHW or channels-last)."""
+    n, c, h, w = t.shape
+    sn, sc, sh, sw = t.stride()
+    return VidcImage(t.data_ptr(), n, c, h, w, sn, sc, sh, sw)
+
+
+def _gravity(I_g: torch.Tensor, I_a: torch.Tensor, device):
+    _require_cuda_f32(I_g, "I_g")
+    _require_cuda_f32(I_a, "I_a")
+    if I_g.device != device or I_a.device != device:
+        raise RuntimeError(f"I_g / I_a must live on {device}, got {I_g.device} / {I_a.device}")
+    B = I_g.shape[0]
+    # the reference does I_g.view(B,3,1), I_a.view(B,1,3)  (:38-39)
+    return I_g.reshape(B, 3).contiguous(), I_a.reshape(I_a.shape[0], 3).contiguous()
+
+
+class _NoBackward(torch.autograd.Function):
+    """Marks outputs as non-differentiable results of a forward-only kernel."""
+
+    @staticmethod
+    def forward(ctx, x, out):
+        return out.view_as(out)
+
+    @staticmethod
+    def backward(ctx, grad):
+        raise NotImplementedError(
+            "vi_depth_completion_b200: the fused warp kernels are forward-only (SURVEY.md section 8 row f4); "
+            "nothing in the reference optimises through the warp (network_run.py:101)")
+
+
+def _attach(x, out):
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _NoBackward.apply(x, out)
+    return out
+
+
+class Warping2DOFAlignment:
+    # networks/warping_2dof_alignment.py:6
+    def __init__(self, fx=577.87061 * 0.5, fy=577.87061 * 0.5, cx=319.87654 * 0.5, cy=239.87603 * 0.5):
+        self.fx = fx
+        self.fy = fy
+        self.cx = cx
+        self.cy = cy
+        self._cam = VidcCamera()
+        check(lib().vidc_camera_init(float(fx), float(fy), float(cx), float(cy), ctypes.byref(self._cam)))
+        self.W = np.int64(self._cam.W)
+        self.H = np.int64(self._cam.H)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        self._const_cache = {}
+        self._ws = {}
+
+    # ---- constant tensors the reference exposes as attributes (:15-24), built lazily ----------
+    def _const(self, name):
+        if name not in self._const_cache:
+            W, H = int(self.W), int(self.H)
+            if name == "K":
+                v = torch.tensor(np.array(self._cam.K, dtype=np.float32).reshape(3, 3))
+            elif name == "K_inv":
+                v = torch.tensor(np.array(self._cam.Kinv, dtype=np.float32).reshape(3, 3))
+            elif name == "XX":
+                v = torch.arange(W, dtype=torch.float32).view(W, 1).expand(W, H).contiguous()
+            elif name == "YY":
+                v = torch.arange(H, dtype=torch.float32).view(1, H).expand(W, H).contiguous()
+            elif name == "corners_points":
+                v = torch.tensor([[0, 0, 1], [W - 1, 0, 1], [0, H - 1, 1], [W - 1, H - 1, 1]], dtype=torch.float32).t()
+            elif name == "I3":
+                v = torch.eye(3, dtype=torch.float32)
+            else:
+                raise AttributeError(name)
+            self._const_cache[name] = v.to(self.device)
+        return self._const_cache[name]
+
+    K = property(lambda self: self._const("K"))
+    K_inv = property(lambda self: self._const("K_inv"))
+    XX = property(lambda self: self._const("XX"))
+    YY = property(lambda self: self._const("YY"))
+    corners_points = property(lambda self: self._const("corners_points"))
+    I3 = property(lambda self: self._const("I3"))
+
+    def _params_ws(self, B, device):
+        key = (device, B)
+        ws = self._ws.get(key)
+        if ws is None:
+            if len(self._ws) > 8:
+                self._ws.clear()
+            ws = torch.empty((max(B, 1), _cabi.FRAME_PARAMS_FLOATS), dtype=torch.float32, device=device)
+            self._ws[key] = ws
+        return ws
+
+    def _skewsymm(self, x):  # :26-32, kept for API compatibility (pure tensor ops, no host sync)
+        x = x.reshape(-1)
+        z = torch.zeros((), dtype=x.dtype, device=x.device)
+        return torch.stack([torch.stack([z, -x[2], x[1]]), torch.stack([x[2], z, -x[0]]), torch.stack([-x[1], x[0], z])]).float()
+
+    # networks/warping_2dof_alignment.py:35-58
+    def _build_homography(self, I_g, I_a):
+        _require_cuda_f32(I_g, "I_g")
+        device = I_g.device
+        g, a = _gravity(I_g, I_a, device)
+        B = g.shape[0]
+        out = torch.empty((3, B, 3, 3), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            check(lib().vidc_build_homography(ctypes.byref(self._cam), g.data_ptr(), a.data_ptr(), B,
+                                              out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), _stream_ptr(device)))
+        return out[0], out[1], out[2]
+
+    def frame_params(self, I_g, I_a):
+        """Additive: the (B,48) per-frame parameter block (vidc_frame_params) as a tensor."""
+        _require_cuda_f32(I_g, "I_g")
+        device = I_g.device
+        g, a = _gravity(I_g, I_a, device)
+        B = g.shape[0]
+        out = torch.empty((B, _cabi.FRAME_PARAMS_FLOATS), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            check(lib().vidc_frame_params_compute(ctypes.byref(self._cam), g.data_ptr(), a.data_ptr(), B, out.data_ptr(),
+                                                  _stream_ptr(device)))
+        return out
+
+    def _empty_like_canvas(self, x):
+        B, C = x.shape[0], x.shape[1]
+        fmt = torch.channels_last if (x.dim() == 4 and C > 1 and x.is_contiguous(memory_format=torch.channels_last)
+                                      and not x.is_contiguous()) else torch.contiguous_format
+        return torch.empty((B, C, int(self.H), int(self.W)), dtype=torch.float32, device=x.device, memory_format=fmt)
+
+    # networks/warping_2dof_alignment.py:108-156
+    def warp_with_gravity_center_aligned(self, x, I_g, I_a, interp_mode='bilinear'):
+        _require_cuda_f32(x, "x")
+        flag_fix_return = False
+        if len(x.shape) == 3:                                   # :110-112
+            x = x.view(x.shape[0], 1, x.shape[1], x.shape[2])
+            flag_fix_return = True
+        if x.dim() != 4:
+            raise RuntimeError(f"x: expected a 3-D or 4-D tensor, got {x.dim()}-D")
+        if interp_mode not in ("bilinear", "nearest"):
+            raise RuntimeError(f"interp_mode must be 'bilinear' or 'nearest', got {interp_mode!r}")
+        device = x.device
+        g, a = _gravity(I_g, I_a, device)
+        y = self._empty_like_canvas(x)
+        Cg_H_C = torch.empty((g.shape[0], 3, 3), dtype=torch.float32, device=device)
+        xi, yi = _image(x), _image(y)
+        with torch.cuda.device(device):
+            check(lib().vidc_warp_forward(ctypes.byref(self._cam), ctypes.byref(xi), g.data_ptr(), a.data_ptr(), g.shape[0],
+                                          _cabi.VIDC_BILINEAR if interp_mode == "bilinear" else _cabi.VIDC_NEAREST,
+                                          self._params_ws(g.shape[0], device).data_ptr(), Cg_H_C.data_ptr(),
+                                          ctypes.byref(yi), _stream_ptr(device)))
+        y = _attach(x, y)
+        if flag_fix_return:                                     # :153-154
+            return Cg_H_C, y.view(x.shape[0], y.shape[2], y.shape[3])
+        return Cg_H_C, y
+
+    # networks/warping_2dof_alignment.py:158-214
+    def image_sampler_forward_inverse(self, I_g, I_a):
+        _require_cuda_f32(I_g, "I_g")
+        device = I_g.device
+        g, a = _gravity(I_g, I_a, device)
+        B = g.shape[0]
+        Rt = torch.empty((B, 3, 3), dtype=torch.float32, device=device)
+        grid = torch.empty((B, int(self.H), int(self.W), 2), dtype=torch.float32, device=device)
+        inv_grid = torch.empty_like(grid)
+        with torch.cuda.device(device):
+            check(lib().vidc_sampler_forward_inverse(ctypes.byref(self._cam), g.data_ptr(), a.data_ptr(), B,
+                                                     self._params_ws(B, device).data_ptr(), Rt.data_ptr(), grid.data_ptr(),
+                                                     inv_grid.data_ptr(), _stream_ptr(device)))
+        return Rt, grid, inv_grid
+
+    # networks/warping_2dof_alignment.py:216-255
+    def inverse_warp_normal_image_with_gravity_center_aligned(self, x, I_g, I_a):
+        return self._unwarp(x, I_g, I_a, normalize=False)[:2]
+
+    def _unwarp(self, x, I_g, I_a, normalize, want_valid=False):
+        _require_cuda_f32(x, "x")
+        if x.dim() != 4:
+            raise RuntimeError(f"x: expected a 4-D tensor, got {x.dim()}-D")
+        device = x.device
+        g, a = _gravity(I_g, I_a, device)
+        z = self._empty_like_canvas(x)
+        Cg_H_C = torch.empty((g.shape[0], 3, 3), dtype=torch.float32, device=device)
+        valid = torch.empty((x.shape[0], 1, int(self.H), int(self.W)), dtype=torch.uint8, device=device) if want_valid else None
+        xi, zi = _image(x), _image(z)
+        with torch.cuda.device(device):
+            check(lib().vidc_unwarp_normals(ctypes.byref(self._cam), ctypes.byref(xi), g.data_ptr(), a.data_ptr(), g.shape[0],
+                                            1 if normalize else 0, self._params_ws(g.shape[0], device).data_ptr(),
+                                            Cg_H_C.data_ptr(), ctypes.byref(zi), valid.data_ptr() if want_valid else None,
+                                            _stream_ptr(device)))
+        return Cg_H_C, _attach(x, z), valid
+
+    # networks/warping_2dof_alignment.py:258-290.  The reference method cannot run (:259 unpacks three
+    # return values into two); this implements its evident intent: forward warp, then z = R y.
+    def warp_normal_image_with_gravity_center_aligned(self, x, I_g, I_a, interp_mode='bilinear'):
+        _require_cuda_f32(x, "x")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise RuntimeError("x: expected (B,3,H,W)")
+        if interp_mode not in ("bilinear", "nearest"):
+            raise RuntimeError(f"interp_mode must be 'bilinear' or 'nearest', got {interp_mode!r}")
+        device = x.device
+        g, a = _gravity(I_g, I_a, device)
+        z = self._empty_like_canvas(x)
+        Cg_H_C = torch.empty((g.shape[0], 3, 3), dtype=torch.float32, device=device)
+        xi, zi = _image(x), _image(z)
+        with torch.cuda.device(device):
+            check(lib().vidc_warp_normals_forward(ctypes.byref(self._cam), ctypes.byref(xi), g.data_ptr(), a.data_ptr(),
+                                                  g.shape[0],
+                                                  _cabi.VIDC_BILINEAR if interp_mode == "bilinear" else _cabi.VIDC_NEAREST,
+                                                  self._params_ws(g.shape[0], device).data_ptr(), Cg_H_C.data_ptr(),
+                                                  ctypes.byref(zi), _stream_ptr(device)))
+        return Cg_H_C, _attach(x, z)
+
+    # networks/warping_2dof_alignment.py:292-310 (numpy single-image variant, non-uniform kw/kh)
+    def warp_with_homography(self, x, Cg_H_C):
+        _require_cuda_f32(x, "x")
+        if x.dim() != 4:
+            raise RuntimeError(f"x: expected a 4-D tensor, got {x.dim()}-D")
+        device = x.device
+        Hm = torch.as_tensor(np.asarray(Cg_H_C.detach().cpu() if isinstance(Cg_H_C, torch.Tensor) else Cg_H_C,
+                                        dtype=np.float32)).reshape(-1, 3, 3)
+        if Hm.shape[0] == 1 and x.shape[0] > 1:
+            Hm = Hm.expand(x.shape[0], 3, 3)
+        Hd = Hm.contiguous().to(device)
+        y = self._empty_like_canvas(x)
+        xi, yi = _image(x), _image(y)
+        with torch.cuda.device(device):
+            check(lib().vidc_warp_with_homography(ctypes.byref(self._cam), ctypes.byref(xi), Hd.data_ptr(), Hd.shape[0],
+                                                  self._params_ws(Hd.shape[0], device).data_ptr(), ctypes.byref(yi),
+                                                  _stream_ptr(device)))
+        return Cg_H_C, _attach(x, y)
+
+    # ---- additive fused entry points ------------------------------------
+    def warp_rgbd(self, x_rgb, x_depth, I_g, I_a, depth_mode='bilinear', with_mask=True, with_coverage=False):
+        """One pass: warp RGB (B,3,h,w) and sparse depth (B,h,w)/(B,1,h,w) into the gravity-aligned canvas and
+        emit the validity mask of surface_normal.py:151.  Returns (Cg_H_C, rgb_w, depth_w, mask_u8[, coverage])."""
+        _require_cuda_f32(x_rgb, "x_rgb")
+        device = x_rgb.device
+        g, a = _gravity(I_g, I_a, device)
+        B = x_rgb.shape[0]
+        squeeze = False
+        di = dwi = None
+        depth_w = None
+        if x_depth is not None:
+            _require_cuda_f32(x_depth, "x_depth")
+            if x_depth.dim() == 3:
+                x_depth = x_depth.view(x_depth.shape[0], 1, x_depth.shape[1], x_depth.shape[2])
+                squeeze = True
+            depth_w = self._empty_like_canvas(x_depth)
+            di, dwi = _image(x_depth), _image(depth_w)
+        rgb_w = self._empty_like_canvas(x_rgb)
+        mask = torch.empty((B, 1, int(self.H), int(self.W)), dtype=torch.uint8, device=device) if with_mask else None
+        cov = torch.empty((B,), dtype=torch.int32, device=device) if with_coverage else None
+        Cg_H_C = torch.empty((g.shape[0], 3, 3), dtype=torch.float32, device=device)
+        ri, rwi = _image(x_rgb), _image(rgb_w)
+        with torch.cuda.device(device):
+            check(lib().vidc_warp_rgbd(ctypes.byref(self._cam), ctypes.byref(ri), ctypes.byref(di) if di is not None else None,
+                                       g.data_ptr(), a.data_ptr(), g.shape[0],
+                                       _cabi.VIDC_BILINEAR if depth_mode == "bilinear" else _cabi.VIDC_NEAREST,
+                                       self._params_ws(g.shape[0], device).data_ptr(), Cg_H_C.data_ptr(),
+                                       ctypes.byref(rwi), ctypes.byref(dwi) if dwi is not None else None,
+                                       mask.data_ptr() if with_mask else None, cov.data_ptr() if with_coverage else None,
+                                       _stream_ptr(device)))
+        if squeeze:
+            depth_w = depth_w.view(B, depth_w.shape[2], depth_w.shape[3])
+        out = (Cg_H_C, rgb_w, depth_w, mask)
+        return out + (cov,) if with_coverage else out
+
+    def unwarp_normals(self, y, I_g, I_a, normalize=True, with_valid=False):
+        """One pass: inverse warp + R^T rotation + F.normalize(dim=1) (surface_normal.py:169-170).
+        Returns (Cg_H_C, n_hat[, valid_u8])."""
+        H, z, valid = self._unwarp(y, I_g, I_a, normalize=normalize, want_valid=with_valid)
+        return (H, z, valid) if with_valid else (H, z)
