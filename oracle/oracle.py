@@ -159,3 +159,19 @@ def normal_stats(norm_gt, pred, mask, normalize_prediction=True):
     lib().vidc_oracle_normal_stats(_p(gt), _p(pred), _p(mask), B, ctypes.c_size_t(hw), int(normalize_prediction), _p(out))
     angle_sum, num, l1 = out
     return {"angle_sum": angle_sum, "num": num, "l1_sum": l1, "loss": l1 / num if num else float("nan")}
+
+
+def warp_unwarp_mt(orc: Oracle, rgb, depth, normals, I_g, I_a, nthreads=1):
+    """One frame step of the whole path (what bench.py times): returns rgb_w, depth_w, mask_u8, normals_cam."""
+    rgb, normals, I_g, I_a = _f32(rgb), _f32(normals), _f32(I_g), _f32(I_a)
+    B = rgb.shape[0]
+    H, W = orc.H, orc.W
+    depth = _f32(depth).reshape(B, H, W) if depth is not None else None
+    rgb_w = np.empty((B, 3, H, W), np.float32)
+    depth_w = np.empty((B, H, W), np.float32) if depth is not None else None
+    mask = np.empty((B, 1, H, W), np.uint8)
+    ncam = np.empty((B, 3, H, W), np.float32)
+    lib().vidc_oracle_warp_unwarp_mt(ctypes.byref(orc.cam), B, int(nthreads), _p(rgb), _p(depth) if depth is not None else None,
+                                     _p(normals), _p(I_g), _p(I_a), _p(rgb_w), _p(depth_w) if depth is not None else None,
+                                     _p(mask), _p(ncam))
+    return rgb_w, depth_w, mask, ncam

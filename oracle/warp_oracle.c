@@ -28,6 +28,7 @@
  * -ffp-contract=off (see oracle/Makefile).
  */
 #include <math.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -485,6 +486,58 @@ float oracle_cosf_mkl_ha(float x)
     fb ^= ybits << 31;
     float out; memcpy(&out, &fb, 4);
     return out;
+}
+
+
+/* ---------------------------------------------------------------------------------------
+ * Batch-parallel wrappers (frames are independent): the reference's CPU path runs with all
+ * host threads torch/MKL give it, so the cpu_baseline / --impl reference legs of bench.py use
+ * these to spread frames over `nthreads` POSIX threads.  Results are identical to the serial
+ * functions (same per-frame code).
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+    const oracle_camera *cam; int B0, B1;
+    const float *rgb, *depth, *normals, *Ig, *Ia;
+    float *rgb_w, *depth_w, *normals_cam; uint8_t *mask;
+} mt_job;
+
+static void *mt_worker(void *arg)
+{
+    mt_job *j = (mt_job *)arg;
+    const oracle_camera *cam = j->cam;
+    const size_t hw = (size_t)cam->H * cam->W;
+    const int n = j->B1 - j->B0;
+    if (n <= 0) return NULL;
+    const size_t o = (size_t)j->B0;
+    vidc_oracle_warp_forward(cam, j->rgb + 3 * hw * o, n, 3, cam->H, cam->W, j->Ig + 3 * o, j->Ia + 3 * o, 0, NULL, j->rgb_w + 3 * hw * o);
+    if (j->depth) vidc_oracle_warp_forward(cam, j->depth + hw * o, n, 1, cam->H, cam->W, j->Ig + 3 * o, j->Ia + 3 * o, 0, NULL, j->depth_w + hw * o);
+    vidc_oracle_mask(j->rgb_w + 3 * hw * o, n, hw, j->mask + hw * o);
+    float *tmp = malloc(sizeof(float) * 3 * hw * (size_t)n);
+    vidc_oracle_inverse_warp_normals(cam, j->normals + 3 * hw * o, n, j->Ig + 3 * o, j->Ia + 3 * o, NULL, tmp);
+    vidc_oracle_normalize(tmp, n, 3, hw, j->normals_cam + 3 * hw * o);
+    free(tmp);
+    return NULL;
+}
+
+/* One "frame step" of the hot path for B frames: warp RGB, warp depth (bilinear), mask,
+   inverse-warp normals, renormalise -- exactly what bench.py times on the GPU. */
+API void vidc_oracle_warp_unwarp_mt(const oracle_camera *cam, int B, int nthreads,
+                                    const float *rgb, const float *depth, const float *normals,
+                                    const float *Ig, const float *Ia,
+                                    float *rgb_w, float *depth_w, uint8_t *mask, float *normals_cam)
+{
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > B) nthreads = B > 0 ? B : 1;
+    pthread_t *th = malloc(sizeof(pthread_t) * (size_t)nthreads);
+    mt_job *jobs = malloc(sizeof(mt_job) * (size_t)nthreads);
+    for (int t = 0; t < nthreads; ++t) {
+        mt_job j = {cam, (int)((long long)B * t / nthreads), (int)((long long)B * (t + 1) / nthreads),
+                    rgb, depth, normals, Ig, Ia, rgb_w, depth_w, normals_cam, mask};
+        jobs[t] = j;
+        pthread_create(&th[t], NULL, mt_worker, &jobs[t]);
+    }
+    for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+    free(jobs); free(th);
 }
 
 /* array wrappers so the tests can sweep the scalar math functions */
