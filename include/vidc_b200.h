@@ -180,6 +180,11 @@ int vidc_warp_unwarp_host(const vidc_camera *cam, int32_t B,
                           void *stream);
 int vidc_release_workspace(void);
 
+/* Test hook: runs the kernels' shared-reciprocal division helpers next to the compiler's IEEE
+   division on n device operand triples (u, v, s); d_out receives 4*n floats
+   [u/s fast | v/s fast | u/s IEEE | v/s IEEE].  Used by tests/test_gpu_math.py only. */
+int vidc_debug_div(const float *d_u, const float *d_v, const float *d_s, int64_t n, float *d_out, void *stream);
+
 /* Number of kernel launches issued by this library since load (all threads). For bench.py's
    gpu_launches accounting. */
 uint64_t vidc_launch_count(void);
