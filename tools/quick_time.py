@@ -38,6 +38,8 @@ def main(cam="S2", B=256, iters=20, roll=30, pitch=30, cl=False):
 
 if __name__ == "__main__":
     main()
+    if len(sys.argv) > 1 and sys.argv[1] == "one":
+        sys.exit(0)
     main(cam="S3", roll=90, pitch=5)
     main(cam="S1", B=64)
     main(cl=True)

@@ -1,8 +1,8 @@
 #!/bin/bash
 # Build-flag sweep on the GPU box: rebuild the library with different tuning macros and time it.
-for cfg in "-DVIDC_MIN_BLOCKS=4" "-DVIDC_MIN_BLOCKS=5" "-DVIDC_MIN_BLOCKS=6" "-DVIDC_MIN_BLOCKS=5 -DVIDC_UNROLL=2" "-DVIDC_MIN_BLOCKS=5 -DVIDC_ROWS=8" "-DVIDC_MIN_BLOCKS=6 -DVIDC_ROWS=2" "-DVIDC_MIN_BLOCKS=3 -DVIDC_UNROLL=4"; do
-  echo "=== $cfg"
+for mb in 3 4 5 6; do for un in 1 2 4; do
+  cfg="-DVIDC_MIN_BLOCKS=$mb -DVIDC_UNROLL=$un"
   VIDC_NVCC_EXTRA="$cfg" python -m vi_depth_completion_b200.build --force > /dev/null || { echo build failed; continue; }
-  python tools/quick_time.py 2>&1 | head -1 | cut -c1-330
-done
+  echo "$cfg $(python tools/quick_time.py one 2>&1 | head -1 | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print("fwd %.3f inv %.3f fps %.0f"%(d["forward_rgbd_mask"]["ms"], d["inverse_rot_norm"]["ms"], d["frames_per_s"]))')"
+done; done
 python -m vi_depth_completion_b200.build --force > /dev/null
