@@ -1,0 +1,116 @@
+"""Generates tests/golden/*.npz by EXECUTING the reference (networks/warping_2dof_alignment.py,
+normal_utils.py, the mask / renormalise lines of networks/surface_normal.py) on CPU in the build
+container.  Run once here; the vectors are committed because /root/reference cannot travel.
+
+    python -m oracle.make_golden
+
+What is frozen
+  golden_tiny.npz   64x48 camera, 12 edge-case + 6 random frames: every intermediate and output IN FULL
+                    (H, R, Hinv, both sampler grids, warped RGB, warped depth bilinear / nearest, un-normalised
+                    and normalised un-warped normals, validity mask, nearest pyramid masks, loss statistics).
+  golden_S1/S2/S3.npz  full-resolution configs of SURVEY.md section 8(d): parameters in full, and for the
+                    large tensors a SHA-256 of the raw fp32 bytes plus 4096 sampled values (bit-exact check
+                    without committing hundreds of MB).
+Inputs are regenerated from seeds by tests/common.py (numpy RandomState), so only outputs are stored.
+"""
+import hashlib
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.ref_loader import REF_ROOT, load_reference_class  # noqa: E402
+from tests import common as C  # noqa: E402
+
+warnings.filterwarnings("ignore")
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def sample_idx(n, k=4096, seed=99):
+    return np.random.RandomState(seed).randint(0, n, size=min(k, n))
+
+
+def load_normal_utils():
+    """normal_utils.py with the undefined `Normalize` bound to F.normalize(x, dim=1)."""
+    import types
+    src = open(os.path.join(REF_ROOT, "normal_utils.py")).read()
+    mod = types.ModuleType("reference_normal_utils")
+    mod.__dict__["Normalize"] = lambda t: F.normalize(t, dim=1)
+    exec(compile(src, "normal_utils.py", "exec"), mod.__dict__)
+    return mod
+
+
+def run_reference(cam_name, I_g, I_a, seed, full):
+    Wref = load_reference_class("cpu")
+    fx, fy, cx, cy = C.CAMERAS[cam_name]
+    w = Wref(fx=fx, fy=fy, cx=cx, cy=cy)
+    B = I_g.shape[0]
+    Hh, Ww = int(w.H), int(w.W)
+    rgb, depth, normals = C.random_images(B, Hh, Ww, seed)
+    sdepth = C.random_images(B, Hh, Ww, seed, sparse_depth=True)[1]
+    g, a = torch.from_numpy(I_g), torch.from_numpy(I_a)
+    with torch.no_grad():
+        H, R, Hi = w._build_homography(g, a)
+        Rt, grid, inv_grid = w.image_sampler_forward_inverse(g, a)
+        _, y = w.warp_with_gravity_center_aligned(torch.from_numpy(rgb), g, a)
+        _, yd = w.warp_with_gravity_center_aligned(torch.from_numpy(depth), g, a)
+        _, ydn = w.warp_with_gravity_center_aligned(torch.from_numpy(sdepth), g, a, interp_mode="nearest")
+        _, z = w.inverse_warp_normal_image_with_gravity_center_aligned(torch.from_numpy(normals), g, a)
+        zn = F.normalize(z, dim=1)                                            # surface_normal.py:170
+        mask = (y[:, 0:1] + y[:, 1:2] + y[:, 2:3] > 1e-2)                     # surface_normal.py:151
+        maskf = mask.float()
+        pyr = [F.interpolate(maskf, size=s, mode="nearest") for s in ((60, 80), (30, 40), (15, 20), (8, 10))]  # :153-156
+        nu = load_normal_utils()
+        gt = F.normalize(torch.from_numpy(C.random_images(B, Hh, Ww, seed + 1000)[2]), dim=1)
+        loss1, ang1 = nu.compute_normal_vectors_loss_l1(gt, z, maskf)
+        loss2, ang2 = nu.compute_normal_vectors_loss_l2(gt, z, maskf)
+    out = {"cam": np.array(C.CAMERAS[cam_name], np.float64), "I_g": I_g, "I_a": I_a, "seed": np.int64(seed),
+           "W": np.int64(Ww), "H": np.int64(Hh), "K": w.K.numpy(), "K_inv": w.K_inv.numpy(),
+           "Hm": H.numpy(), "R": R.numpy(), "Hinv": Hi.numpy(), "Rt_guard": Rt.numpy(),
+           "stats": np.array([float(loss1), float(ang1), float(loss2), float(ang2), float(maskf.sum())], np.float64)}
+    big = {"grid": grid.numpy(), "inv_grid": inv_grid.numpy(), "y_rgb": y.numpy(), "y_depth": yd.numpy(),
+           "y_sdepth_nearest": ydn.numpy(), "z": z.numpy(), "zn": zn.numpy(), "mask": mask.numpy().astype(np.uint8)}
+    for i, p in enumerate(pyr):
+        big[f"pyr{i}"] = p.numpy().astype(np.uint8)
+    if full:
+        out.update(big)
+    else:
+        for k, v in big.items():
+            flat = v.reshape(-1)
+            idx = sample_idx(flat.size)
+            out[k + "_sha256"] = np.array(sha(v))
+            out[k + "_idx"] = idx.astype(np.int64)
+            out[k + "_val"] = flat[idx]
+            out[k + "_shape"] = np.array(v.shape, np.int64)
+    return out
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    # tiny: edge cases + random, everything in full
+    eg, ea = C.edge_case_gravity()
+    rg, ra = C.random_gravity(6, seed=4321, roll_deg=60, pitch_deg=45)
+    np.savez_compressed(os.path.join(OUT, "golden_tiny.npz"),
+                        **run_reference("tiny", np.concatenate([eg, rg]), np.concatenate([ea, ra]), seed=7, full=True))
+    # full-resolution configs: digests
+    for name, (B, roll, pitch, seed) in {"S1": (6, 30, 30, 1), "S2": (3, 30, 30, 2), "S3": (3, 75, 40, 3)}.items():
+        I_g, I_a = C.random_gravity(B, seed=1234, roll_deg=roll, pitch_deg=pitch)
+        if name == "S3":
+            xg, xa = C.extreme_roll_gravity(3, seed=5)
+            I_g, I_a = np.concatenate([I_g, xg]), np.concatenate([I_a, xa])
+        np.savez_compressed(os.path.join(OUT, f"golden_{name}.npz"), **run_reference(name, I_g, I_a, seed, full=False))
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

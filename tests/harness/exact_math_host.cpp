@@ -20,3 +20,13 @@ size_t host_atan2f_sweep_vs_libm(uint32_t ylo, uint32_t yhi, uint32_t ystep, flo
     return bad;
 }
 }
+
+// Host build of the product's per-frame parameter code (csrc/frame_params.cuh): the same source the
+// params kernel compiles for the device, so goldens can pin it without a GPU.
+#include "../../vi_depth_completion_b200/csrc/frame_params.cuh"
+extern "C" void host_frame_params(const vidc_camera* cam, const float* Ig, const float* Ia, int B, vidc_frame_params* out) {
+    for (int i = 0; i < B; ++i) {
+        memset(&out[i], 0, sizeof(vidc_frame_params));
+        vidc::frame_params_from_gravity(*cam, Ig + 3 * i, Ia + 3 * i, out[i]);
+    }
+}

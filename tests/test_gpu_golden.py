@@ -1,0 +1,102 @@
+"""The CUDA path against the golden vectors frozen from the EXECUTED reference (tests/golden, made by
+oracle/make_golden.py in the build container).  Bar: masks bit-exact, RGB / depth within 1e-4, normals within
+0.01 degrees -- and, because the kernels restate the reference's roundings, identical bits / SHA-256."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import common as C
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _cuda_outputs(g, dev):
+    from vi_depth_completion_b200.warping_2dof_alignment import Warping2DOFAlignment
+    from vi_depth_completion_b200 import normal_utils as NU
+    fx, fy, cx, cy = [float(v) for v in g["cam"]]
+    w = Warping2DOFAlignment(fx=fx, fy=fy, cx=cx, cy=cy)
+    I_g, I_a, seed = g["I_g"], g["I_a"], int(g["seed"])
+    B = I_g.shape[0]
+    Hh, Ww = int(w.H), int(w.W)
+    rgb, depth, normals = C.random_images(B, Hh, Ww, seed)
+    sdepth = C.random_images(B, Hh, Ww, seed, sparse_depth=True)[1]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    gg, aa = t(I_g), t(I_a)
+    H, R, Hi = w._build_homography(gg, aa)
+    Rt, grid, inv = w.image_sampler_forward_inverse(gg, aa)
+    _, y = w.warp_with_gravity_center_aligned(t(rgb), gg, aa)
+    _, yd = w.warp_with_gravity_center_aligned(t(depth), gg, aa)
+    _, ydn = w.warp_with_gravity_center_aligned(t(sdepth), gg, aa, interp_mode="nearest")
+    _, z = w.inverse_warp_normal_image_with_gravity_center_aligned(t(normals), gg, aa)
+    _, zn = w.unwarp_normals(t(normals), gg, aa, normalize=True)
+    _, rgb_w, depth_w, mask = w.warp_rgbd(t(rgb), t(depth), gg, aa)
+    maskf = NU.validity_mask(y)
+    pyr = NU.pyramid_masks(maskf)
+    gt = torch.nn.functional.normalize(t(C.random_images(B, Hh, Ww, seed + 1000)[2]), dim=1)
+    loss1, ang1 = NU.compute_normal_vectors_loss_l1(gt, z, maskf)
+    loss2, ang2 = NU.compute_normal_vectors_loss_l2(gt, z, maskf)
+    n = lambda x: x.detach().cpu().numpy()
+    out = {"K": n(w.K), "K_inv": n(w.K_inv), "Hm": n(H), "R": n(R), "Hinv": n(Hi), "Rt_guard": n(Rt), "grid": n(grid),
+           "inv_grid": n(inv), "y_rgb": n(y), "y_depth": n(yd), "y_sdepth_nearest": n(ydn), "z": n(z), "zn": n(zn),
+           "mask": n(mask), "rgb_w": n(rgb_w), "depth_w": n(depth_w), "maskf": n(maskf).astype(np.uint8)}
+    for i, p in enumerate(pyr):
+        out[f"pyr{i}"] = n(p).astype(np.uint8)
+    out["stats"] = [float(loss1), float(ang1), float(loss2), float(ang2), float(maskf.sum())]
+    return out
+
+
+SMALL = ["K", "K_inv", "Hm", "R", "Hinv", "Rt_guard"]
+BIG = ["grid", "inv_grid", "y_rgb", "y_depth", "y_sdepth_nearest", "z", "zn", "mask", "pyr0", "pyr1", "pyr2", "pyr3"]
+
+
+def test_cuda_matches_reference_tiny_full(cuda_device):
+    g = np.load(os.path.join(GOLD, "golden_tiny.npz"))
+    out = _cuda_outputs(g, cuda_device)
+    # north-star tolerances first
+    assert np.array_equal(out["mask"].astype(np.uint8).reshape(g["mask"].shape), g["mask"])
+    assert np.nanmax(np.abs(out["y_rgb"] - g["y_rgb"])) <= 1e-4
+    assert np.nanmax(np.abs(out["y_depth"] - g["y_depth"])) <= 1e-4
+    err, ok = C.angular_error_deg(out["zn"], g["zn"])
+    assert err.size == 0 or err.max() <= 0.01
+    # and the stronger bit-level statement
+    for k in SMALL + BIG:
+        a, b = out[k], g[k]
+        if b.dtype == np.uint8:
+            assert np.array_equal(a.astype(np.uint8).reshape(b.shape), b), k
+        else:
+            assert C.count_bit_mismatches(a.reshape(b.shape), b) == 0, f"CUDA output differs from the executed reference in {k}"
+    assert C.count_bit_mismatches(out["rgb_w"], g["y_rgb"]) == 0
+    assert C.count_bit_mismatches(out["depth_w"].reshape(g["y_depth"].shape), g["y_depth"]) == 0
+    assert np.array_equal(out["maskf"].reshape(g["mask"].shape), g["mask"])
+    loss1, ang1, loss2, ang2, msum = g["stats"]
+    s = out["stats"]
+    assert s[4] == msum
+    assert s[0] == pytest.approx(loss1, rel=1e-5) and s[1] == pytest.approx(ang1, rel=1e-5)
+    assert s[2] == pytest.approx(loss2, rel=1e-5) and s[3] == pytest.approx(ang2, rel=1e-5)
+
+
+@pytest.mark.parametrize("name", ["S1", "S2", "S3"])
+def test_cuda_matches_reference_full_resolution_digests(cuda_device, name):
+    g = np.load(os.path.join(GOLD, f"golden_{name}.npz"))
+    out = _cuda_outputs(g, cuda_device)
+    for k in SMALL:
+        assert C.count_bit_mismatches(out[k], g[k]) == 0, k
+    for k in BIG:
+        v = out[k]
+        v = v.astype(np.uint8) if str(g[k + "_val"].dtype) == "uint8" else v.astype(np.float32)
+        v = v.reshape(tuple(g[k + "_shape"]))
+        got, want = v.reshape(-1)[g[k + "_idx"]], g[k + "_val"]
+        if v.dtype == np.uint8:
+            assert np.array_equal(got, want), k
+        else:
+            assert np.nanmax(np.abs(got - want)) <= 1e-4, k
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"sampled bits differ in {k}"
+        assert _sha(v) == str(g[k + "_sha256"]), f"SHA-256 of {k} differs from the executed reference"
