@@ -115,7 +115,7 @@ class ClockSampler:
 
 def make_inputs(rank, B):
     cam = C.CAMERAS[WORKLOAD]
-    I_g, I_a = C.random_gravity(B, seed=1234 + rank, roll_deg=30.0, pitch_deg=30.0)
+    I_g, I_a = C.random_gravity(B, seed=1234 + rank, roll_deg=30.0, pitch_deg=30.0)   # sharding.rank_seed(1234, rank)
     return cam, I_g, I_a
 
 
@@ -157,7 +157,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from vi_depth_completion_b200 import _cabi
+    from vi_depth_completion_b200 import _cabi, sharding
     from vi_depth_completion_b200.warping_2dof_alignment import Warping2DOFAlignment
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -219,11 +219,8 @@ def run_ours(args):
     elapsed_ms = e_start.elapsed_time(e_end)
     fwd_ms = float(np.mean([ev[k][0].elapsed_time(ev[k][1]) for k in range(K)]))
     inv_ms = float(np.mean([ev[k][1].elapsed_time(ev[k][2]) for k in range(K)]))
-    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    value = world * B * K / (elapsed_ms * 1e-3)
+    # frames are independent: aggregate = sum(frames) / max(elapsed) over ranks, no data-path collective
+    _, elapsed_ms, value = sharding.aggregate_throughput(B * K, elapsed_ms, dev)
 
     # ---- e2e: C-ABI host-buffer entry point, pinned host memory, H2D + kernels + D2H timed --------
     hw = H * W
@@ -251,10 +248,7 @@ def run_ours(args):
         e2e_step()                  # synchronises its stream before returning
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * Ke / float(t.item())
+    _, _, e2e_value = sharding.aggregate_throughput(B * Ke, e2e_s * 1e3, dev)
     # sanity: the e2e path returns the same bits as the resident path
     _, rgb_w, depth_w, mask = w.warp_rgbd(rgb, depth, g, a)
     torch.cuda.synchronize()
