@@ -284,7 +284,8 @@ def run_ours(args):
         traffic = ncu_traffic()
         roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "peak_source": peak_src,
-                    "traffic": (traffic or {}).get(dom[0]),
+                    "traffic": ((traffic or {}).get(dom[0]) or {}).get("dram_bytes_total"),
+                    "traffic_source": ((traffic or {}).get(dom[0]) or {}).get("source"),
                     "algorithmic_bytes_per_launch": px * dom[2],
                     "kernels": {"warp_rgbd_fast_kernel": {"ms": fwd_ms, "GBps": px * BYTES_PER_PX_FWD / fwd_ms / 1e6},
                                 "unwarp_normals_fast_kernel": {"ms": inv_ms, "GBps": px * BYTES_PER_PX_INV / inv_ms / 1e6}},
