@@ -191,3 +191,36 @@ def test_empty_batch(cuda_device):
     g = torch.zeros(0, 3, device=cuda_device)
     H, y = w.warp_with_gravity_center_aligned(torch.zeros(0, 3, 240, 320, device=cuda_device), g, g)
     assert y.shape == (0, 3, 240, 320) and H.shape == (0, 3, 3)
+
+
+def test_tma_staged_forward_kernel_matches_oracle(cuda_device, oracle_mod):
+    """The opt-in TMA-staged forward kernel (VIDC_TMA=1, cp.async.bulk.tensor footprint staging) in a fresh process:
+    same bits as the oracle, including tiles that fall back (extreme roll) and exterior tiles."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from tests import common as C
+from oracle import oracle as O
+from vi_depth_completion_b200.warping_2dof_alignment import Warping2DOFAlignment
+dev = torch.device("cuda", 0)
+for cam, (I_g, I_a) in (("S1", C.random_gravity(6, 1234)), ("S2", C.random_gravity(3, 77)), ("S3", C.extreme_roll_gravity(7, 3)),
+                        ("tiny", C.edge_case_gravity())):
+    w, o = Warping2DOFAlignment(*C.CAMERAS[cam]), O.Oracle(*C.CAMERAS[cam])
+    B = I_g.shape[0]
+    rgb, depth, _ = C.random_images(B, o.H, o.W, 5)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    for mode in ("bilinear", "nearest"):
+        _, rgb_w, depth_w, mask = w.warp_rgbd(t(rgb), t(depth), t(I_g), t(I_a), depth_mode=mode)
+        _, oy = o.warp_with_gravity_center_aligned(rgb, I_g, I_a)
+        _, od = o.warp_with_gravity_center_aligned(depth, I_g, I_a, interp_mode=mode)
+        assert C.count_bit_mismatches(rgb_w.cpu().numpy(), oy) == 0, (cam, mode, "rgb")
+        assert C.count_bit_mismatches(depth_w.cpu().numpy()[:, 0], od) == 0, (cam, mode, "depth")
+        assert np.array_equal(mask.cpu().numpy(), O.validity_mask(oy)), (cam, mode, "mask")
+print("TMA_OK")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VIDC_TMA="1")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "TMA_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]

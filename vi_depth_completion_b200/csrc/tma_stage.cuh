@@ -1,0 +1,54 @@
+// tma_stage.cuh -- Blackwell/Hopper TMA staging of a tile's source footprint into shared memory.
+//
+// The gather of the warp kernels is limited by the L1 data pipe: a 32-lane bilinear tap load touches
+// ~3.6 cache lines, 12-16 such requests per row segment.  Here ONE thread issues a tiled bulk tensor copy
+// (cp.async.bulk.tensor, SASS UTMALDG) of the footprint's bounding box -- all planes at once, completion
+// on an mbarrier -- and the taps are then read from shared memory with immediate offsets and no bounds
+// tests: the TMA unit zero-fills everything outside the tensor, which IS padding_mode='zeros'.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace vidc_k {
+
+constexpr int TMA_BW = 64;                           // box width in floats (smem row pitch)
+constexpr int TMA_NH = 4;                            // box-height classes
+__host__ __device__ constexpr int tma_box_h(int cls) { return cls == 0 ? 24 : cls == 1 ? 32 : cls == 2 ? 40 : 48; }
+constexpr int TMA_BH_MAX = 48;
+
+struct TmaMaps {                                     // one tensor map per box-height class
+    CUtensorMap a[TMA_NH];                           // planes of image A (RGB or normals), box (64, h, C, 1)
+    CUtensorMap d[TMA_NH];                           // depth, box (64, h, 1, 1)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // make the init visible to the async (TMA) proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t phase) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    }
+}
+// 4-D tiled load: coordinates (x, y, plane, frame); out-of-range elements are written as zeros.
+// Measured on the B200 (tools/tma_probe4.cu): x * sizeof(float) must be a multiple of 16 bytes -- an unaligned
+// innermost coordinate raises 'illegal instruction'; negative and out-of-range coordinates are fine.
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, unsigned long long* bar,
+                                            int x, int y, int c, int n) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(smem_u32(smem_dst)), "l"((unsigned long long)map), "r"(x), "r"(y), "r"(c), "r"(n), "r"(smem_u32(bar))
+        : "memory");
+}
+
+}  // namespace vidc_k
