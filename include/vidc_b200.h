@@ -94,6 +94,12 @@ const char *vidc_last_error(void);
 /* Replaces Warping2DOFAlignment.__init__ (:6-24).  Host only. */
 int vidc_camera_init(double fx, double fy, double cx, double cy, vidc_camera *cam);
 
+/* Dataset-side gravity conditioning on device: raw IMU gravity (B,3) -> I_g, I_a.
+   rule 0 = Azure / Demo loaders (dataset.py:334-345, :472-483: negate y and z; psi < 1e-4 or cos(pitch) > 0.707
+            -> a = [0,1,0], else a = [0, cos(pitch), sin(pitch)]);
+   rule 1 = ScanNet compute_alignment_tensor (dataset.py:45-55: psi < 1e-6 or cos(pitch) <= 0.3 -> a = g, else [0,1,0]). */
+int vidc_condition_gravity(const float *d_raw, int32_t B, int32_t rule, float *d_Ig, float *d_Ia, void *stream);
+
 /* Replaces _build_homography (:35-58) plus the per-frame bbox / scale block (:125-140).
    d_Ig, d_Ia: (B,3) contiguous.  d_params: B entries. One thread per frame, no host sync. */
 int vidc_frame_params_compute(const vidc_camera *cam, const float *d_Ig, const float *d_Ia, int32_t B,
@@ -123,6 +129,14 @@ int vidc_warp_rgbd(const vidc_camera *cam, const vidc_image *rgb, const vidc_ima
                    vidc_frame_params *d_params_ws, float *d_H_out,
                    const vidc_image *rgb_out, const vidc_image *depth_out,
                    uint8_t *d_mask_u8, uint32_t *d_coverage, void *stream);
+
+/* Packed variant of vidc_warp_rgbd for callers that hold RGB + depth interleaved: d_in is (B, Hin, Win, 4) fp32
+   (channels-last, C = 4: R, G, B, depth), d_out is (B, cam.H, cam.W, 4); both contiguous and 16-byte aligned.
+   Every bilinear tap is one 128-bit load and every pixel one 128-bit store.  Same results per channel. */
+int vidc_warp_rgbd_packed(const vidc_camera *cam, const float *d_in, int32_t B, int32_t Hin, int32_t Win,
+                          const float *d_Ig, const float *d_Ia, int32_t B_gravity, vidc_interp depth_mode,
+                          vidc_frame_params *d_params_ws, float *d_H_out, float *d_out, uint8_t *d_mask_u8,
+                          uint32_t *d_coverage, void *stream);
 
 /* Replaces inverse_warp_normal_image_with_gravity_center_aligned (:216-255) and, when
    `normalize` != 0, also the caller's F.normalize(z, dim=1) (surface_normal.py:170) in the same

@@ -94,6 +94,46 @@ def run_reference(cam_name, I_g, I_a, seed, full):
     return out
 
 
+def reference_gravity_rules():
+    """The dataset-side gravity conditioning, taken verbatim from the reference source text and executed:
+    dataset.py:45-55 (compute_alignment_tensor, ScanNet) and dataset.py:473-483 (Demo loader, identical to :335-345)."""
+    import ast
+    import textwrap
+    src = open(os.path.join(REF_ROOT, "dataset.py")).read()
+    lines = src.splitlines()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "compute_alignment_tensor"][0]
+    ns = {"torch": torch, "np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "dataset.py", "exec"), ns)
+    block = textwrap.dedent("\n".join(lines[472:483]))          # 1-based lines 473..483
+    assert block.startswith("gravity_tensor[1] = -gravity_tensor[1]") and "alignment_tensor" in block, block
+
+    def azure(raw):
+        loc = {"gravity_tensor": torch.tensor(raw, dtype=torch.float), "torch": torch}
+        exec(block, loc)
+        return loc["gravity_tensor"].numpy().copy(), loc["alignment_tensor"].numpy().copy()
+
+    def scannet(raw):
+        g = torch.tensor(raw, dtype=torch.float)
+        return g.numpy().copy(), ns["compute_alignment_tensor"](g).numpy().copy()
+    return azure, scannet
+
+
+def gravity_cases():
+    rs = np.random.RandomState(2025)
+    raw = rs.randn(512, 3).astype(np.float32)
+    raw /= np.linalg.norm(raw, axis=1, keepdims=True).astype(np.float32)
+    # near the thresholds: pitch ~ 45 deg (cos 0.707), cos(pitch) ~ 0.3, psi ~ 1e-4 / 1e-6, demo-like vectors
+    extra = []
+    for p in np.linspace(0.70, 0.72, 41):
+        extra.append([0.05, -np.float32(p), -np.float32(np.sqrt(max(0.0, 1 - p * p - 0.0025)))])
+    for p in np.linspace(0.29, 0.31, 21):
+        extra.append([0.1, np.float32(p), np.float32(np.sqrt(1 - p * p - 0.01))])
+    for e in (1e-2, 9.9e-3, 1.01e-2, 1e-3, 7e-4, 0.0):
+        extra.append([1.0, np.float32(e), 0.0]); extra.append([1.0, 0.0, -np.float32(e)])
+    extra += [[0.09, -0.99, 0.19], [-0.09, -0.99, -0.19], [0.0, -1.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [0.0, 0.0, -1.0]]
+    return np.concatenate([raw, np.array(extra, np.float32)]).astype(np.float32)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     # tiny: edge cases + random, everything in full
@@ -108,6 +148,12 @@ def main():
             xg, xa = C.extreme_roll_gravity(3, seed=5)
             I_g, I_a = np.concatenate([I_g, xg]), np.concatenate([I_a, xa])
         np.savez_compressed(os.path.join(OUT, f"golden_{name}.npz"), **run_reference(name, I_g, I_a, seed, full=False))
+    raw = gravity_cases()
+    azure, scannet = reference_gravity_rules()
+    ga = [azure(r) for r in raw]; gs = [scannet(r) for r in raw]
+    np.savez_compressed(os.path.join(OUT, "golden_gravity.npz"), raw=raw,
+                        azure_g=np.stack([x[0] for x in ga]), azure_a=np.stack([x[1] for x in ga]),
+                        scannet_g=np.stack([x[0] for x in gs]), scannet_a=np.stack([x[1] for x in gs]))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -175,3 +175,12 @@ def warp_unwarp_mt(orc: Oracle, rgb, depth, normals, I_g, I_a, nthreads=1):
                                      _p(normals), _p(I_g), _p(I_a), _p(rgb_w), _p(depth_w) if depth is not None else None,
                                      _p(mask), _p(ncam))
     return rgb_w, depth_w, mask, ncam
+
+
+# dataset.py:45-55 (rule='scannet'), :334-345 / :472-483 (rule='azure')
+def condition_gravity(raw, rule="azure"):
+    raw = _f32(raw)
+    B = raw.shape[0]
+    Ig = np.empty((B, 3), np.float32); Ia = np.empty((B, 3), np.float32)
+    lib().vidc_oracle_condition_gravity(_p(raw), B, 0 if rule == "azure" else 1, _p(Ig), _p(Ia))
+    return Ig, Ia

@@ -46,6 +46,7 @@ typedef struct {
 
 /* torch.cos on CPU == MKL VML vmsCos HA; restated near the end of this file */
 float oracle_cosf_mkl_ha(float d);
+float oracle_sinf_mkl_ha(float d);
 
 /* ref :6-24 */
 API void vidc_oracle_camera_init(double fx, double fy, double cx, double cy, oracle_camera *cam)
@@ -538,6 +539,70 @@ API void vidc_oracle_warp_unwarp_mt(const oracle_camera *cam, int B, int nthread
     }
     for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
     free(jobs); free(th);
+}
+
+
+/* torch.sin on a CPU float tensor == MKL VML vmsSin(VML_HA); same structure and constants as the cosine:
+   N = rint(|x| / pi), r = |x| - N pi (fp64), sin x = sign(x) (-1)^N (float)(r + r (r^2 P(r^2))). */
+float oracle_sinf_mkl_ha(float x)
+{
+    const float INVPI = 0x1.45f306p-2f, SHIFTER = 0x1.8p+23f;
+    const double PI_HI = 0x1.921fb5444p+1, PI_LO = 0x1.68c234c4c6629p-38;
+    const double C3 = -0x1.55554bc836587p-3, C5 = 0x1.110ed3804ca96p-7,
+                 C7 = -0x1.9f6ffeea73463p-13, C9 = 0x1.5dbdf0e4c7deep-19;
+    uint32_t xb; memcpy(&xb, &x, 4);
+    const float ax = fabsf(x);
+    const float y = fmaf(ax, INVPI, SHIFTER);
+    uint32_t ybits; memcpy(&ybits, &y, 4);
+    const float n = y - SHIFTER;
+    const double dn = (double)n;
+    double r = (double)ax;
+    r = fma(-PI_HI, dn, r);
+    r = fma(-dn, PI_LO, r);
+    const double r2 = r * r;
+    double p = fma(C9, r2, C7);
+    p = fma(r2, p, C5);
+    p = fma(r2, p, C3);
+    const double q = p * r2;
+    const float f = (float)fma(r, q, r);
+    uint32_t fb; memcpy(&fb, &f, 4);
+    fb ^= (ybits << 31) ^ (xb & 0x80000000u);
+    float out; memcpy(&out, &fb, 4);
+    return out;
+}
+API void vidc_oracle_sinf_array(const float *in, size_t n, float *out)
+{
+    for (size_t i = 0; i < n; ++i) out[i] = oracle_sinf_mkl_ha(in[i]);
+}
+
+/* dataset.py gravity conditioning.
+   rule 0: Azure / Demo loaders (:334-345, :472-483): flip y,z; psi < 1e-4 -> a = [0,1,0];
+           cos(pitch) > 0.707 -> [0,1,0] else [0, cos(pitch), sin(pitch)].
+   rule 1: ScanNet compute_alignment_tensor (:45-55), no flip: psi < 1e-6 -> a = g; cos(pitch) > 0.3 -> [0,1,0] else a = g. */
+API void vidc_oracle_condition_gravity(const float *raw, int B, int rule, float *Ig, float *Ia)
+{
+    for (int i = 0; i < B; ++i) {
+        float g0 = raw[3 * i], g1 = raw[3 * i + 1], g2 = raw[3 * i + 2];
+        if (rule == 0) { g1 = -g1; g2 = -g2; }
+        const float a1 = g1 * g1, a2 = g2 * g2;
+        const float psi = a1 + a2;
+        float a[3] = {0.0f, 1.0f, 0.0f};
+        if (rule == 0) {
+            if (!(psi < 1e-4f)) {
+                const float pitch = atan2f(g2, g1);
+                const float c = oracle_cosf_mkl_ha(pitch);
+                if (!(c > 0.707f)) { a[0] = 0.0f; a[1] = c; a[2] = oracle_sinf_mkl_ha(pitch); }
+            }
+        } else {
+            if (psi < 1e-6f) { a[0] = g0; a[1] = g1; a[2] = g2; }
+            else {
+                const float pitch = atan2f(g2, g1);
+                if (!(oracle_cosf_mkl_ha(pitch) > 0.3f)) { a[0] = g0; a[1] = g1; a[2] = g2; }
+            }
+        }
+        Ig[3 * i] = g0; Ig[3 * i + 1] = g1; Ig[3 * i + 2] = g2;
+        Ia[3 * i] = a[0]; Ia[3 * i + 1] = a[1]; Ia[3 * i + 2] = a[2];
+    }
 }
 
 /* array wrappers so the tests can sweep the scalar math functions */

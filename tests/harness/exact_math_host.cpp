@@ -30,3 +30,10 @@ extern "C" void host_frame_params(const vidc_camera* cam, const float* Ig, const
         vidc::frame_params_from_gravity(*cam, Ig + 3 * i, Ia + 3 * i, out[i]);
     }
 }
+
+extern "C" void host_condition_gravity(const float* raw, int B, int rule, float* Ig, float* Ia) {
+    for (int i = 0; i < B; ++i) vidc::condition_gravity(raw + 3 * i, rule, Ig + 3 * i, Ia + 3 * i);
+}
+extern "C" void host_mkl_sinf_ha(const float* x, size_t n, float* out) {
+    for (size_t i = 0; i < n; ++i) out[i] = vidc::mkl_sinf_ha(x[i]);
+}

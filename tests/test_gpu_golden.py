@@ -100,3 +100,13 @@ def test_cuda_matches_reference_full_resolution_digests(cuda_device, name):
             assert np.nanmax(np.abs(got - want)) <= 1e-4, k
             assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"sampled bits differ in {k}"
         assert _sha(v) == str(g[k + "_sha256"]), f"SHA-256 of {k} differs from the executed reference"
+
+
+@pytest.mark.parametrize("rule", ["azure", "scannet"])
+def test_cuda_gravity_conditioning_matches_reference(cuda_device, rule):
+    """Row f1: raw IMU gravity -> (I_g, I_a) on device, bit-identical to the reference's dataset code."""
+    from vi_depth_completion_b200.gravity import condition_gravity
+    g = np.load(os.path.join(GOLD, "golden_gravity.npz"))
+    Ig, Ia = condition_gravity(torch.from_numpy(g["raw"]).to(cuda_device), rule)
+    assert C.count_bit_mismatches(Ig.cpu().numpy(), g[rule + "_g"]) == 0
+    assert C.count_bit_mismatches(Ia.cpu().numpy(), g[rule + "_a"]) == 0

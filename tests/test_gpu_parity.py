@@ -250,3 +250,22 @@ def test_host_buffer_entry_point_pipelined(cuda_device, oracle_mod):
         assert np.array_equal(outs[2].numpy(), o_mask)
         assert C.count_bit_mismatches(outs[3].numpy(), o_n) == 0
     assert _cabi.lib().vidc_release_workspace() == 0
+
+
+def test_packed_rgbd_nhwc4_matches_oracle(cuda_device, oracle_mod):
+    """Opt-in packed layout (channels-last, C = 4): one 128-bit load per tap; per-channel results identical."""
+    for cam_name, (I_g, I_a) in (("S1", C.random_gravity(5, 91)), ("S3", C.extreme_roll_gravity(7, 3)), ("tiny", C.edge_case_gravity())):
+        w, o = _mk(cam_name, cuda_device)
+        B = I_g.shape[0]
+        rgb, depth, _ = C.random_images(B, o.H, o.W, 13, sparse_depth=(cam_name == "S1"))
+        x = torch.cat([_t(rgb, cuda_device), _t(depth, cuda_device)[:, None]], 1).contiguous(memory_format=torch.channels_last)
+        for mode in ("bilinear", "nearest"):
+            _, y, mask, cov = w.warp_rgbd_packed(x, _t(I_g, cuda_device), _t(I_a, cuda_device), depth_mode=mode, with_coverage=True)
+            assert y.is_contiguous(memory_format=torch.channels_last)
+            _, oy = o.warp_with_gravity_center_aligned(rgb, I_g, I_a)
+            _, od = o.warp_with_gravity_center_aligned(depth, I_g, I_a, interp_mode=mode)
+            yn = y.cpu().numpy()
+            assert C.count_bit_mismatches(yn[:, :3], oy) == 0
+            assert C.count_bit_mismatches(yn[:, 3], od) == 0
+            assert np.array_equal(mask.cpu().numpy(), oracle_mod.validity_mask(oy))
+            assert np.array_equal(cov.cpu().numpy(), mask.cpu().numpy().reshape(B, -1).sum(1))

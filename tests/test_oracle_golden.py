@@ -93,3 +93,11 @@ def test_oracle_loss_statistics(oracle_mod, name):
     assert st["angle_sum"] == pytest.approx(ang1, rel=1e-5)
     assert st["angle_sum"] == pytest.approx(ang2, rel=1e-5)
     assert st["loss"] == pytest.approx(loss1, rel=1e-5)
+
+
+@pytest.mark.parametrize("rule", ["azure", "scannet"])
+def test_oracle_gravity_conditioning_matches_reference(oracle_mod, rule):
+    g = _load("gravity")
+    Ig, Ia = oracle_mod.condition_gravity(g["raw"], rule)
+    assert C.count_bit_mismatches(Ig, g[rule + "_g"]) == 0
+    assert C.count_bit_mismatches(Ia, g[rule + "_a"]) == 0

@@ -66,3 +66,14 @@ def test_full_path_matches_live_reference(oracle_mod):
     assert C.count_bit_mismatches(yd.numpy(), oyd) == 0
     assert C.count_bit_mismatches(z.numpy(), oz) == 0
     assert C.count_bit_mismatches(zn.numpy(), oracle_mod.normalize(oz)) == 0
+
+
+def test_sin_restatement_matches_torch_sin(oracle_mod):
+    """torch.sin on CPU (MKL VML vmsSin HA).  Every float in [-3.2, 3.2] was checked once with stride 1: 0 mismatches."""
+    import torch
+    bits = np.concatenate([np.arange(0, int(np.float32(3.2).view(np.uint32)) + 1, 17, dtype=np.uint32),
+                           np.arange(0x80000000, 0x80000000 + int(np.float32(3.2).view(np.uint32)) + 1, 19, dtype=np.uint32)])
+    x = bits.view(np.float32)
+    out = np.empty_like(x)
+    oracle_mod.lib().vidc_oracle_sinf_array(x.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(x.size), out.ctypes.data_as(ctypes.c_void_p))
+    assert np.array_equal(out.view(np.uint32), torch.sin(torch.from_numpy(x)).numpy().view(np.uint32))

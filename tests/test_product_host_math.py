@@ -79,3 +79,24 @@ def test_product_params_match_oracle_random(hlib, oracle_mod):
         assert C.count_bit_mismatches(prm[:, 9:18].reshape(B, 3, 3), R) == 0
         assert C.count_bit_mismatches(prm[:, 18:27].reshape(B, 3, 3), Hi) == 0
         assert C.count_bit_mismatches(prm[:, 27:35], sc) == 0
+
+
+@pytest.mark.parametrize("rule,idx", [("azure", 0), ("scannet", 1)])
+def test_product_gravity_conditioning_matches_reference_golden(hlib, rule, idx):
+    """dataset.py:45-55 / :472-483: the product's device function, host build."""
+    g = np.load(os.path.join(GOLD, "golden_gravity.npz"))
+    raw = np.ascontiguousarray(g["raw"])
+    Ig, Ia = np.empty_like(raw), np.empty_like(raw)
+    hlib.host_condition_gravity(_p(raw), raw.shape[0], idx, _p(Ig), _p(Ia))
+    assert C.count_bit_mismatches(Ig, g[rule + "_g"]) == 0
+    assert C.count_bit_mismatches(Ia, g[rule + "_a"]) == 0
+
+
+def test_mkl_sin_restatement_vs_oracle(hlib, oracle_mod):
+    bits = np.concatenate([np.arange(0, int(np.float32(3.2).view(np.uint32)) + 1, 97, dtype=np.uint32),
+                           np.arange(0x80000000, 0x80000000 + int(np.float32(3.2).view(np.uint32)) + 1, 101, dtype=np.uint32)])
+    x = bits.view(np.float32)
+    a, b = np.empty_like(x), np.empty_like(x)
+    hlib.host_mkl_sinf_ha(_p(x), ctypes.c_size_t(x.size), _p(a))
+    oracle_mod.lib().vidc_oracle_sinf_array(_p(x), ctypes.c_size_t(x.size), _p(b))
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))

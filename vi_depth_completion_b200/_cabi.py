@@ -53,6 +53,9 @@ _SIGNATURES = {
     "vidc_warp_rgbd": (ctypes.c_int, [_P(VidcCamera), _P(VidcImage), _P(VidcImage), c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int,
                                       ctypes.c_void_p, c_f32p, _P(VidcImage), _P(VidcImage), ctypes.c_void_p, ctypes.c_void_p,
                                       ctypes.c_void_p]),
+    "vidc_warp_rgbd_packed": (ctypes.c_int, [_P(VidcCamera), c_f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_f32p, c_f32p,
+                                             ctypes.c_int32, ctypes.c_int, ctypes.c_void_p, c_f32p, c_f32p, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p]),
     "vidc_unwarp_normals": (ctypes.c_int, [_P(VidcCamera), _P(VidcImage), c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int32,
                                            ctypes.c_void_p, c_f32p, _P(VidcImage), ctypes.c_void_p, ctypes.c_void_p]),
     "vidc_sampler_forward_inverse": (ctypes.c_int, [_P(VidcCamera), c_f32p, c_f32p, ctypes.c_int32, ctypes.c_void_p, c_f32p,
@@ -67,6 +70,7 @@ _SIGNATURES = {
     "vidc_normal_stats": (ctypes.c_int, [_P(VidcImage), _P(VidcImage), _P(VidcImage), ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
     "vidc_warp_unwarp_host": (ctypes.c_int, [_P(VidcCamera), ctypes.c_int32] + [ctypes.c_void_p] * 10),
     "vidc_release_workspace": (ctypes.c_int, []),
+    "vidc_condition_gravity": (ctypes.c_int, [c_f32p, ctypes.c_int32, ctypes.c_int32, c_f32p, c_f32p, ctypes.c_void_p]),
     "vidc_debug_div": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, ctypes.c_int64, c_f32p, ctypes.c_void_p]),
 }
 

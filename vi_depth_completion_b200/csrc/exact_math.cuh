@@ -183,4 +183,49 @@ VIDC_HD float mkl_cosf_ha(float x) {
     return u2f(f2u(f) ^ (f2u(y) << 31));
 }
 
+
+// ---- MKL VML vmsSin, VML_HA (same reduction / polynomial as the cosine; behind torch.sin on CPU tensors,
+//      dataset.py:345,:483) ----
+VIDC_HD float mkl_sinf_ha(float x) {
+    const float INVPI = u2f(0x3ea2f983u), SHIFTER = u2f(0x4b400000u);
+    const double PI_HI = 0x1.921fb5444p+1, PI_LO = 0x1.68c234c4c6629p-38;
+    const double C3 = -0x1.55554bc836587p-3, C5 = 0x1.110ed3804ca96p-7,
+                 C7 = -0x1.9f6ffeea73463p-13, C9 = 0x1.5dbdf0e4c7deep-19;
+    const float ax = fabsf(x);
+    const float y = fmaf(ax, INVPI, SHIFTER);
+    const float n = y - SHIFTER;
+    const double dn = (double)n;
+    double r = (double)ax;
+    r = fma(-PI_HI, dn, r);
+    r = fma(-dn, PI_LO, r);
+    const double r2 = r * r;
+    double p = fma(C9, r2, C7);
+    p = fma(r2, p, C5);
+    p = fma(r2, p, C3);
+    const double q = p * r2;
+    const float f = (float)fma(r, q, r);
+    return u2f(f2u(f) ^ (f2u(y) << 31) ^ (f2u(x) & 0x80000000u));
+}
+
+// ---- dataset-side gravity conditioning (dataset.py:45-55 rule 1, :334-345 / :472-483 rule 0) ----
+VIDC_HD void condition_gravity(const float* raw, int rule, float* g, float* a) {
+    float g0 = raw[0], g1 = raw[1], g2 = raw[2];
+    if (rule == 0) { g1 = -g1; g2 = -g2; }                       // :473-474
+    const float s1 = g1 * g1, s2 = g2 * g2;
+    const float psi = s1 + s2;                                   // :475
+    a[0] = 0.0f; a[1] = 1.0f; a[2] = 0.0f;
+    if (rule == 0) {
+        if (!(psi < 1e-4f)) {                                    // :476
+            const float pitch = glibc_atan2f(g2, g1);            // :479
+            const float c = mkl_cosf_ha(pitch);
+            if (!(c > 0.707f)) { a[1] = c; a[2] = mkl_sinf_ha(pitch); }   // :480-483
+        }
+    } else {
+        bool keep_g = psi < 1e-6f;                               // :47-48
+        if (!keep_g) keep_g = !(mkl_cosf_ha(glibc_atan2f(g2, g1)) > 0.3f);   // :50-54
+        if (keep_g) { a[0] = g0; a[1] = g1; a[2] = g2; }
+    }
+    g[0] = g0; g[1] = g1; g[2] = g2;
+}
+
 }  // namespace vidc

@@ -301,6 +301,28 @@ class Warping2DOFAlignment:
         out = (Cg_H_C, rgb_w, depth_w, mask)
         return out + (cov,) if with_coverage else out
 
+    def warp_rgbd_packed(self, x_rgbd, I_g, I_a, depth_mode='bilinear', with_mask=True, with_coverage=False):
+        """Packed RGBD forward warp: x_rgbd is (B,4,h,w) in channels-last memory format (R,G,B,depth interleaved, 16 B per
+        pixel), so each bilinear tap is one 128-bit load.  Returns (Cg_H_C, y_rgbd channels-last, mask_u8[, coverage])."""
+        _require_cuda_f32(x_rgbd, "x_rgbd")
+        if x_rgbd.dim() != 4 or x_rgbd.shape[1] != 4 or not x_rgbd.is_contiguous(memory_format=torch.channels_last):
+            raise RuntimeError("x_rgbd: expected a (B,4,H,W) tensor in torch.channels_last memory format")
+        device = x_rgbd.device
+        g, a = _gravity(I_g, I_a, device)
+        B, _, h, w = x_rgbd.shape
+        y = torch.empty((B, 4, int(self.H), int(self.W)), dtype=torch.float32, device=device, memory_format=torch.channels_last)
+        mask = torch.empty((B, 1, int(self.H), int(self.W)), dtype=torch.uint8, device=device) if with_mask else None
+        cov = torch.empty((B,), dtype=torch.int32, device=device) if with_coverage else None
+        Cg_H_C = torch.empty((g.shape[0], 3, 3), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            check(lib().vidc_warp_rgbd_packed(ctypes.byref(self._cam), x_rgbd.data_ptr(), B, h, w, g.data_ptr(), a.data_ptr(),
+                                              g.shape[0], _cabi.VIDC_BILINEAR if depth_mode == "bilinear" else _cabi.VIDC_NEAREST,
+                                              self._params_ws(g.shape[0], device).data_ptr(), Cg_H_C.data_ptr(), y.data_ptr(),
+                                              mask.data_ptr() if with_mask else None, cov.data_ptr() if with_coverage else None,
+                                              _stream_ptr(device)))
+        out = (Cg_H_C, y, mask)
+        return out + (cov,) if with_coverage else out
+
     def unwarp_normals(self, y, I_g, I_a, normalize=True, with_valid=False):
         """One pass: inverse warp + R^T rotation + F.normalize(dim=1) (surface_normal.py:169-170).
         Returns (Cg_H_C, n_hat[, valid_u8])."""
