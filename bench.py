@@ -222,6 +222,20 @@ def run_ours(args):
     # frames are independent: aggregate = sum(frames) / max(elapsed) over ranks, no data-path collective
     _, elapsed_ms, value = sharding.aggregate_throughput(B * K, elapsed_ms, dev)
 
+    # ---- informational: the opt-in packed layout (channels-last RGBD, one 128-bit load per tap), same frames ----
+    packed = torch.cat([rgb, depth], 1).contiguous(memory_format=torch.channels_last)
+    for _ in range(3):
+        w.warp_rgbd_packed(packed, g, a)
+    torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(K):
+        w.warp_rgbd_packed(packed, g, a)
+    p1.record()
+    torch.cuda.synchronize()
+    packed_ms = p0.elapsed_time(p1) / K
+    del packed
+
     # ---- e2e: C-ABI host-buffer entry point, pinned host memory, H2D + kernels + D2H timed --------
     hw = H * W
     h_rgb = torch.empty(B, 3, H, W, pin_memory=True); h_rgb.copy_(rgb)
@@ -288,7 +302,10 @@ def run_ours(args):
                     "traffic_source": ((traffic or {}).get(dom[0]) or {}).get("source"),
                     "algorithmic_bytes_per_launch": px * dom[2],
                     "kernels": {"warp_rgbd_fast_kernel": {"ms": fwd_ms, "GBps": px * BYTES_PER_PX_FWD / fwd_ms / 1e6},
-                                "unwarp_normals_fast_kernel": {"ms": inv_ms, "GBps": px * BYTES_PER_PX_INV / inv_ms / 1e6}},
+                                "unwarp_normals_fast_kernel": {"ms": inv_ms, "GBps": px * BYTES_PER_PX_INV / inv_ms / 1e6},
+                                "warp_rgbd_nhwc4_kernel (opt-in packed RGBD layout, not part of `value`)": {
+                                    "ms": packed_ms, "GBps": px * BYTES_PER_PX_FWD / packed_ms / 1e6,
+                                    "frac": px * BYTES_PER_PX_FWD / packed_ms / 1e6 / peak}},
                     "step": {"bytes_per_frame": H * W * (BYTES_PER_PX_FWD + BYTES_PER_PX_INV),
                              "achieved": value / world * H * W * (BYTES_PER_PX_FWD + BYTES_PER_PX_INV) / 1e9,
                              "frac": value / world * H * W * (BYTES_PER_PX_FWD + BYTES_PER_PX_INV) / 1e9 / peak}}
