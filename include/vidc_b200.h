@@ -172,6 +172,12 @@ int vidc_validity_mask(const vidc_image *x1, uint8_t *d_mask_u8, float *d_mask_f
 int vidc_mask_nearest(const float *d_mask, int32_t B, int32_t Hin, int32_t Win,
                       int32_t Hout, int32_t Wout, float *d_out, void *stream);
 
+/* surface_normal.py:153-156, all levels in ONE launch: source mask either uint8 (as written by
+   vidc_warp_rgbd) or float; sizes_hw = {H0, W0, H1, W1, ...} (host array, 1..4 levels); d_outs = host array of `levels`
+   device pointers to float (B,1,Hl,Wl) outputs. */
+int vidc_mask_pyramid(const uint8_t *d_mask_u8, const float *d_mask_f32, int32_t B, int32_t Hin, int32_t Win,
+                      int32_t levels, const int32_t *sizes_hw, float *const *d_outs, void *stream);
+
 /* surface_normal.py:170: F.normalize(z, dim=1) for 3-channel images. */
 int vidc_normalize3(const vidc_image *z, const vidc_image *out, void *stream);
 

@@ -40,6 +40,8 @@ def _cuda_outputs(g, dev):
     _, rgb_w, depth_w, mask = w.warp_rgbd(t(rgb), t(depth), gg, aa)
     maskf = NU.validity_mask(y)
     pyr = NU.pyramid_masks(maskf)
+    pyr_from_u8 = NU.pyramid_masks(mask)                      # same levels straight from the fused kernel's uint8 mask
+    assert all(torch.equal(p, q) for p, q in zip(pyr, pyr_from_u8))
     gt = torch.nn.functional.normalize(t(C.random_images(B, Hh, Ww, seed + 1000)[2]), dim=1)
     loss1, ang1 = NU.compute_normal_vectors_loss_l1(gt, z, maskf)
     loss2, ang2 = NU.compute_normal_vectors_loss_l2(gt, z, maskf)

@@ -66,6 +66,8 @@ _SIGNATURES = {
                                                  _P(VidcImage), ctypes.c_void_p]),
     "vidc_validity_mask": (ctypes.c_int, [_P(VidcImage), ctypes.c_void_p, c_f32p, ctypes.c_void_p, ctypes.c_void_p]),
     "vidc_mask_nearest": (ctypes.c_int, [c_f32p] + [ctypes.c_int32] * 5 + [c_f32p, ctypes.c_void_p]),
+    "vidc_mask_pyramid": (ctypes.c_int, [ctypes.c_void_p, c_f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                         ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
     "vidc_normalize3": (ctypes.c_int, [_P(VidcImage), _P(VidcImage), ctypes.c_void_p]),
     "vidc_normal_stats": (ctypes.c_int, [_P(VidcImage), _P(VidcImage), _P(VidcImage), ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
     "vidc_warp_unwarp_host": (ctypes.c_int, [_P(VidcCamera), ctypes.c_int32] + [ctypes.c_void_p] * 10),

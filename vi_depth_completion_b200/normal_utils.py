@@ -87,14 +87,21 @@ def validity_mask(x1, as_float=True, with_coverage=False):
 
 # networks/surface_normal.py:153-156
 def pyramid_masks(feature_mask, sizes=PYRAMID_SIZES):
-    """F.interpolate(feature_mask, size=s, mode='nearest') for each pyramid level."""
-    _require_cuda_f32(feature_mask, "feature_mask")
+    """F.interpolate(feature_mask, size=s, mode='nearest') for every pyramid level, ONE kernel launch.
+    feature_mask: (B,1,H,W) float32 (as the reference builds it) or the uint8 mask written by warp_rgbd."""
+    if not isinstance(feature_mask, torch.Tensor) or not feature_mask.is_cuda:
+        raise RuntimeError("feature_mask: expected a CUDA tensor (this module has no CPU fallback)")
+    if feature_mask.dtype not in (torch.float32, torch.uint8):
+        raise RuntimeError(f"feature_mask: expected float32 or uint8, got {feature_mask.dtype}")
+    if len(sizes) < 1 or len(sizes) > 4:
+        raise RuntimeError("pyramid_masks: 1..4 levels")
     m = feature_mask.contiguous()
     B, _, Hin, Win = m.shape
-    outs = []
+    outs = [torch.empty((B, 1, int(h), int(w)), dtype=torch.float32, device=m.device) for (h, w) in sizes]
+    flat = (ctypes.c_int32 * (2 * len(sizes)))(*[int(v) for hw in sizes for v in hw])
+    ptrs = (ctypes.c_void_p * len(sizes))(*[o.data_ptr() for o in outs])
     with torch.cuda.device(m.device):
-        for (Ho, Wo) in sizes:
-            o = torch.empty((B, 1, Ho, Wo), dtype=torch.float32, device=m.device)
-            check(lib().vidc_mask_nearest(m.data_ptr(), B, Hin, Win, Ho, Wo, o.data_ptr(), _stream_ptr(m.device)))
-            outs.append(o)
+        check(lib().vidc_mask_pyramid(m.data_ptr() if m.dtype == torch.uint8 else None,
+                                      m.data_ptr() if m.dtype == torch.float32 else None,
+                                      B, Hin, Win, len(sizes), flat, ptrs, _stream_ptr(m.device)))
     return outs
