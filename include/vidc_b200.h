@@ -146,6 +146,15 @@ int vidc_unwarp_normals(const vidc_camera *cam, const vidc_image *x, const float
                         int32_t B_gravity, int32_t normalize, vidc_frame_params *d_params_ws,
                         float *d_H_out, const vidc_image *z, uint8_t *d_valid_u8, void *stream);
 
+/* Backward of the two warps w.r.t. the sampled image (in the reference this is torch autograd
+   through F.grid_sample, :152 / :251, and the bmm at :253).  grad_out: (B,C,cam.H,cam.W), any strides.
+   inverse == 0: backward of warp_with_gravity_center_aligned  -> d_grad_in (B,C,Hin,Win) contiguous, zeroed by the call;
+   inverse != 0: backward of inverse_warp_normal_image_...     -> grad w.r.t. x (B,3,H,W): scatter of R * grad_out.
+   Scatter-add with atomics (as ATen's CUDA backward): results agree with autograd to rounding, not bit-for-bit. */
+int vidc_warp_backward(const vidc_camera *cam, const vidc_image *grad_out, const float *d_Ig, const float *d_Ia,
+                       int32_t B_gravity, int32_t inverse, vidc_interp mode, vidc_frame_params *d_params_ws,
+                       float *d_grad_in, int32_t Hin, int32_t Win, void *stream);
+
 /* Replaces image_sampler_forward_inverse (:158-214) including the aspect guard (:178-187).
    d_Rt (B,3,3), d_grid / d_inv_grid (B,H,W,2) contiguous; any may be NULL. */
 int vidc_sampler_forward_inverse(const vidc_camera *cam, const float *d_Ig, const float *d_Ia, int32_t B,

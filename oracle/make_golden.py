@@ -134,6 +134,36 @@ def gravity_cases():
     return np.concatenate([raw, np.array(extra, np.float32)]).astype(np.float32)
 
 
+def backward_golden():
+    """Row f4: gradients of the executed reference (torch autograd through grid_sample / bmm on CPU)."""
+    Wref = load_reference_class("cpu")
+    fx, fy, cx, cy = C.CAMERAS["tiny"]
+    w = Wref(fx=fx, fy=fy, cx=cx, cy=cy)
+    I_g, I_a = C.random_gravity(6, seed=777, roll_deg=50, pitch_deg=35)
+    Hh, Ww = int(w.H), int(w.W)
+    rgb, depth, normals = C.random_images(6, Hh, Ww, seed=31)
+    wt = np.random.RandomState(5).randn(6, 3, Hh, Ww).astype(np.float32)      # upstream gradient
+    g, a = torch.from_numpy(I_g), torch.from_numpy(I_a)
+    out = {"cam": np.array(C.CAMERAS["tiny"], np.float64), "I_g": I_g, "I_a": I_a, "seed": np.int64(31), "wt_seed": np.int64(5)}
+    x = torch.from_numpy(rgb).requires_grad_(True)
+    _, y = w.warp_with_gravity_center_aligned(x, g, a)
+    (y * torch.from_numpy(wt)).sum().backward()
+    out["grad_forward_rgb"] = x.grad.numpy().copy()
+    d = torch.from_numpy(depth).requires_grad_(True)
+    _, yd = w.warp_with_gravity_center_aligned(d, g, a)
+    (yd * torch.from_numpy(wt[:, 0])).sum().backward()
+    out["grad_forward_depth"] = d.grad.numpy().copy()
+    n = torch.from_numpy(normals).requires_grad_(True)
+    _, z = w.inverse_warp_normal_image_with_gravity_center_aligned(n, g, a)
+    (z * torch.from_numpy(wt)).sum().backward()
+    out["grad_inverse_normals"] = n.grad.numpy().copy()
+    n2 = torch.from_numpy(normals).requires_grad_(True)
+    _, z2 = w.inverse_warp_normal_image_with_gravity_center_aligned(n2, g, a)
+    (F.normalize(z2, dim=1) * torch.from_numpy(wt)).sum().backward()           # through surface_normal.py:170 as well
+    out["grad_inverse_normals_normalized"] = n2.grad.numpy().copy()
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     # tiny: edge cases + random, everything in full
@@ -148,6 +178,7 @@ def main():
             xg, xa = C.extreme_roll_gravity(3, seed=5)
             I_g, I_a = np.concatenate([I_g, xg]), np.concatenate([I_a, xa])
         np.savez_compressed(os.path.join(OUT, f"golden_{name}.npz"), **run_reference(name, I_g, I_a, seed, full=False))
+    np.savez_compressed(os.path.join(OUT, "golden_tiny_backward.npz"), **backward_golden())
     raw = gravity_cases()
     azure, scannet = reference_gravity_rules()
     ga = [azure(r) for r in raw]; gs = [scannet(r) for r in raw]

@@ -112,3 +112,36 @@ def test_cuda_gravity_conditioning_matches_reference(cuda_device, rule):
     Ig, Ia = condition_gravity(torch.from_numpy(g["raw"]).to(cuda_device), rule)
     assert C.count_bit_mismatches(Ig.cpu().numpy(), g[rule + "_g"]) == 0
     assert C.count_bit_mismatches(Ia.cpu().numpy(), g[rule + "_a"]) == 0
+
+
+def test_cuda_backward_matches_reference_autograd(cuda_device):
+    """Row f4: gradients w.r.t. the sampled image against torch autograd through the EXECUTED reference (CPU).
+    The CUDA backward scatters with atomics, so the tolerance is rounding-level, not bit-exact: 2e-5 absolute on
+    gradients of magnitude O(1..10)."""
+    from vi_depth_completion_b200.warping_2dof_alignment import Warping2DOFAlignment
+    g = np.load(os.path.join(GOLD, "golden_tiny_backward.npz"))
+    fx, fy, cx, cy = [float(v) for v in g["cam"]]
+    w = Warping2DOFAlignment(fx=fx, fy=fy, cx=cx, cy=cy)
+    I_g, I_a = g["I_g"], g["I_a"]
+    B, Hh, Ww = I_g.shape[0], int(w.H), int(w.W)
+    rgb, depth, normals = C.random_images(B, Hh, Ww, int(g["seed"]))
+    wt = np.random.RandomState(int(g["wt_seed"])).randn(B, 3, Hh, Ww).astype(np.float32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    gg, aa, wtt = t(I_g), t(I_a), t(wt)
+    x = t(rgb).requires_grad_(True)
+    _, y = w.warp_with_gravity_center_aligned(x, gg, aa)
+    (y * wtt).sum().backward()
+    assert np.abs(x.grad.cpu().numpy() - g["grad_forward_rgb"]).max() <= 2e-5
+    d = t(depth).requires_grad_(True)
+    _, yd = w.warp_with_gravity_center_aligned(d, gg, aa)
+    (yd * wtt[:, 0]).sum().backward()
+    assert np.abs(d.grad.cpu().numpy() - g["grad_forward_depth"]).max() <= 2e-5
+    n = t(normals).requires_grad_(True)
+    _, z = w.inverse_warp_normal_image_with_gravity_center_aligned(n, gg, aa)
+    (z * wtt).sum().backward()
+    assert np.abs(n.grad.cpu().numpy() - g["grad_inverse_normals"]).max() <= 2e-5
+    n2 = t(normals).requires_grad_(True)
+    _, z2 = w.inverse_warp_normal_image_with_gravity_center_aligned(n2, gg, aa)
+    (torch.nn.functional.normalize(z2, dim=1) * wtt).sum().backward()      # torch's normalize backward on top of ours
+    ref = g["grad_inverse_normals_normalized"]
+    assert np.abs(n2.grad.cpu().numpy() - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())

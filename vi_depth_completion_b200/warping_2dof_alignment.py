@@ -55,8 +55,35 @@ def _gravity(I_g: torch.Tensor, I_a: torch.Tensor, device):
     return I_g.reshape(B, 3).contiguous(), I_a.reshape(I_a.shape[0], 3).contiguous()
 
 
+class _WarpFn(torch.autograd.Function):
+    """Connects the forward-only fused kernels to autograd: backward is the scatter kernel of vidc_warp_backward
+    (gradient w.r.t. the sampled image only -- the gravity tensors come from the DataLoader and carry no gradient,
+    exactly as in the reference, where only self.cnn parameters are optimised, network_run.py:101)."""
+
+    @staticmethod
+    def forward(ctx, x, out, warper, g, a, inverse, mode):
+        ctx.warper, ctx.inverse, ctx.mode = warper, inverse, mode
+        ctx.in_shape = tuple(x.shape)
+        ctx.save_for_backward(g, a)
+        return out.view_as(out)
+
+    @staticmethod
+    def backward(ctx, grad):
+        g, a = ctx.saved_tensors
+        w = ctx.warper
+        B, C, Hin, Win = ctx.in_shape
+        grad = grad.float()
+        gx = torch.empty((B, C, Hin, Win), dtype=torch.float32, device=grad.device)
+        gi = _image(grad)
+        with torch.cuda.device(grad.device):
+            check(lib().vidc_warp_backward(ctypes.byref(w._cam), ctypes.byref(gi), g.data_ptr(), a.data_ptr(), g.shape[0],
+                                           1 if ctx.inverse else 0, ctx.mode, w._params_ws(g.shape[0], grad.device).data_ptr(),
+                                           gx.data_ptr(), Hin, Win, _stream_ptr(grad.device)))
+        return gx, None, None, None, None, None, None
+
+
 class _NoBackward(torch.autograd.Function):
-    """Marks outputs as non-differentiable results of a forward-only kernel."""
+    """Outputs of fused entry points that have no backward kernel (renormalising unwarp, rotated forward warp)."""
 
     @staticmethod
     def forward(ctx, x, out):
@@ -65,12 +92,14 @@ class _NoBackward(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad):
         raise NotImplementedError(
-            "vi_depth_completion_b200: the fused warp kernels are forward-only (SURVEY.md section 8 row f4); "
-            "nothing in the reference optimises through the warp (network_run.py:101)")
+            "vi_depth_completion_b200: this fused entry point is forward-only; use the reference-shaped methods "
+            "(warp_with_gravity_center_aligned / inverse_warp_normal_image_with_gravity_center_aligned) to train through the warp")
 
 
-def _attach(x, out):
+def _attach(x, out, warper=None, g=None, a=None, inverse=False, mode=0):
     if torch.is_grad_enabled() and x.requires_grad:
+        if warper is not None:
+            return _WarpFn.apply(x, out, warper, g, a, inverse, mode)
         return _NoBackward.apply(x, out)
     return out
 
@@ -184,7 +213,7 @@ class Warping2DOFAlignment:
                                           _cabi.VIDC_BILINEAR if interp_mode == "bilinear" else _cabi.VIDC_NEAREST,
                                           self._params_ws(g.shape[0], device).data_ptr(), Cg_H_C.data_ptr(),
                                           ctypes.byref(yi), _stream_ptr(device)))
-        y = _attach(x, y)
+        y = _attach(x, y, self, g, a, False, _cabi.VIDC_BILINEAR if interp_mode == "bilinear" else _cabi.VIDC_NEAREST)
         if flag_fix_return:                                     # :153-154
             return Cg_H_C, y.view(x.shape[0], y.shape[2], y.shape[3])
         return Cg_H_C, y
@@ -223,7 +252,8 @@ class Warping2DOFAlignment:
                                             1 if normalize else 0, self._params_ws(g.shape[0], device).data_ptr(),
                                             Cg_H_C.data_ptr(), ctypes.byref(zi), valid.data_ptr() if want_valid else None,
                                             _stream_ptr(device)))
-        return Cg_H_C, _attach(x, z), valid
+        z = _attach(x, z, self, g, a, True, _cabi.VIDC_BILINEAR) if not normalize else _attach(x, z)
+        return Cg_H_C, z, valid
 
     # networks/warping_2dof_alignment.py:258-290.  The reference method cannot run (:259 unpacks three
     # return values into two); this implements its evident intent: forward warp, then z = R y.
