@@ -219,6 +219,12 @@ for cam, (I_g, I_a) in (("S1", C.random_gravity(6, 1234)), ("S2", C.random_gravi
         assert C.count_bit_mismatches(rgb_w.cpu().numpy(), oy) == 0, (cam, mode, "rgb")
         assert C.count_bit_mismatches(depth_w.cpu().numpy(), od) == 0, (cam, mode, "depth")
         assert np.array_equal(mask.cpu().numpy(), O.validity_mask(oy)), (cam, mode, "mask")
+    nrm = C.random_images(B, o.H, o.W, 6)[2]
+    _, z = w.inverse_warp_normal_image_with_gravity_center_aligned(t(nrm), t(I_g), t(I_a))
+    _, nh, valid = w.unwarp_normals(t(nrm), t(I_g), t(I_a), with_valid=True)
+    _, oz = o.inverse_warp_normal_image_with_gravity_center_aligned(nrm, I_g, I_a)
+    assert C.count_bit_mismatches(z.cpu().numpy(), oz) == 0, (cam, "unwarp")
+    assert C.count_bit_mismatches(nh.cpu().numpy(), O.normalize(oz)) == 0, (cam, "unwarp+normalize")
 print("TMA_OK")
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, VIDC_TMA="1")
