@@ -76,7 +76,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -215,7 +215,7 @@ def run_ours(args):
     e_end.record()
     barrier()
     launches = lib.vidc_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    n_clock_rows_timed = len(sampler.rows) if rank == 0 else 0    # samples taken while the K timed steps ran
     elapsed_ms = e_start.elapsed_time(e_end)
     fwd_ms = float(np.mean([ev[k][0].elapsed_time(ev[k][1]) for k in range(K)]))
     inv_ms = float(np.mean([ev[k][1].elapsed_time(ev[k][2]) for k in range(K)]))
@@ -263,6 +263,9 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     _, _, e2e_value = sharding.aggregate_throughput(B * Ke, e2e_s * 1e3, dev)
+    clocks = sampler.stop() if rank == 0 else None             # window: timed steps + packed kernel + e2e steps
+    if clocks is not None:
+        clocks["samples_during_timed_steps"] = n_clock_rows_timed
     # sanity: the e2e path returns the same bits as the resident path
     _, rgb_w, depth_w, mask = w.warp_rgbd(rgb, depth, g, a)
     torch.cuda.synchronize()
@@ -332,7 +335,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     args = ap.parse_args()
