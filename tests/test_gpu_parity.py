@@ -275,3 +275,54 @@ def test_packed_rgbd_nhwc4_matches_oracle(cuda_device, oracle_mod):
             assert C.count_bit_mismatches(yn[:, 3], od) == 0
             assert np.array_equal(mask.cpu().numpy(), oracle_mod.validity_mask(oy))
             assert np.array_equal(cov.cpu().numpy(), mask.cpu().numpy().reshape(B, -1).sum(1))
+
+
+@pytest.mark.parametrize("intr", [(120.0, 118.0, 100.3, 70.2), (90.0, 95.0, 33.4, 47.9), (300.0, 300.0, 256.0, 128.0)])
+def test_odd_canvas_sizes(cuda_device, oracle_mod, intr):
+    """Canvas sizes that are not multiples of the 32x32 tile (201x141, 67x96) and a wide 512x256 one: the fast kernels'
+    runtime-geometry instantiation and the generic-stride kernels, inputs of a different size than the canvas, strided views."""
+    from vi_depth_completion_b200.warping_2dof_alignment import Warping2DOFAlignment
+    fx, fy, cx, cy = intr
+    w, o = Warping2DOFAlignment(fx=fx, fy=fy, cx=cx, cy=cy), oracle_mod.Oracle(fx, fy, cx, cy)
+    assert (int(w.W), int(w.H)) == (o.W, o.H)
+    B = 5
+    I_g, I_a = C.random_gravity(B, seed=8, roll_deg=40, pitch_deg=30)
+    rgb, depth, normals = C.random_images(B, o.H, o.W, seed=3)
+    g, a = _t(I_g, cuda_device), _t(I_a, cuda_device)
+    _, rgb_w, depth_w, mask = w.warp_rgbd(_t(rgb, cuda_device), _t(depth, cuda_device), g, a)
+    _, nhat = w.unwarp_normals(_t(normals, cuda_device), g, a)
+    o_rgb, o_depth, o_mask, o_n = oracle_mod.warp_unwarp_mt(o, rgb, depth, normals, I_g, I_a, 2)
+    assert C.count_bit_mismatches(rgb_w.cpu().numpy(), o_rgb) == 0
+    assert C.count_bit_mismatches(depth_w.cpu().numpy(), o_depth) == 0
+    assert np.array_equal(mask.cpu().numpy(), o_mask)
+    assert C.count_bit_mismatches(nhat.cpu().numpy(), o_n) == 0
+    # a differently sized, non-contiguous input view (every second column of a wider buffer): generic-stride kernel
+    wide = C.random_images(B, o.H + 7, 2 * (o.W + 5), seed=4)[0]
+    view = _t(wide, cuda_device)[:, :, :, ::2]
+    assert not view.is_contiguous()
+    _, y = w.warp_with_gravity_center_aligned(view, g, a)
+    _, oy = o.warp_with_gravity_center_aligned(np.ascontiguousarray(wide[:, :, :, ::2]), I_g, I_a)
+    assert C.count_bit_mismatches(y.cpu().numpy(), oy) == 0
+
+
+def test_cuda_graph_capture(cuda_device, oracle_mod):
+    """The whole step is capturable in a CUDA graph (no host synchronisation, no allocation outside torch's pool):
+    the launch-bound small-batch case replays as one graph launch and returns the same bits."""
+    w, o = _mk("S1", cuda_device)
+    B = 8
+    I_g, I_a = C.random_gravity(B, seed=12)
+    rgb, depth, normals = C.random_images(B, o.H, o.W, seed=9)
+    x, d, n, g, a = (_t(v, cuda_device) for v in (rgb, depth, normals, I_g, I_a))
+    w.warp_rgbd(x, d, g, a); w.unwarp_normals(n, g, a)          # warm the workspace caches outside the capture
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        _, rgb_w, depth_w, mask = w.warp_rgbd(x, d, g, a)
+        _, nhat = w.unwarp_normals(n, g, a)
+    x.copy_(_t(C.random_images(B, o.H, o.W, seed=10)[0], cuda_device))      # new input, same buffers
+    graph.replay()
+    torch.cuda.synchronize()
+    _, oy = o.warp_with_gravity_center_aligned(x.cpu().numpy(), I_g, I_a)
+    _, oz = o.inverse_warp_normal_image_with_gravity_center_aligned(normals, I_g, I_a)
+    assert C.count_bit_mismatches(rgb_w.cpu().numpy(), oy) == 0
+    assert C.count_bit_mismatches(nhat.cpu().numpy(), oracle_mod.normalize(oz)) == 0
