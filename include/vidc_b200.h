@@ -73,7 +73,9 @@ typedef struct vidc_frame_params {
     float kw, kh;          /* :135-140 */
     float ikw, ikh;        /* "1./kw", "1./kh"  :142-143 */
     float w_max, h_max;    /* :132-133 */
-    float reserved[13];
+    float fwd_col_major;   /* 1.0 when output rows of the forward warp run along source columns (|roll| > 45 deg): kernels transpose their thread mapping */
+    float inv_col_major;   /* same for the inverse warp */
+    float reserved[11];
 } vidc_frame_params;
 
 /* Logical (N, C, H, W) image batch with element strides. */

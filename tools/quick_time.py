@@ -34,7 +34,7 @@ def main(cam="S2", B=256, iters=20, roll=30, pitch=30, cl=False):
     tot = res["forward_rgbd_mask"]["ms"] + res["inverse_rot_norm"]["ms"]
     res["frames_per_s"] = B / tot * 1e3
     res["frac_of_6546.6"] = B * H * W * 57 / tot / 1e6 / 6546.6
-    print(json.dumps({"cam": cam, "B": B, "cl": cl, "roll": roll, **res}))
+    print(json.dumps({"cam": cam, "B": B, "cl": cl, "roll": roll, **res}), flush=True)
 
 if __name__ == "__main__":
     main()
