@@ -102,6 +102,14 @@ int vidc_camera_init(double fx, double fy, double cx, double cy, vidc_camera *ca
    rule 1 = ScanNet compute_alignment_tensor (dataset.py:45-55: psi < 1e-6 or cos(pitch) <= 0.3 -> a = g, else [0,1,0]). */
 int vidc_condition_gravity(const float *d_raw, int32_t B, int32_t rule, float *d_Ig, float *d_Ia, void *stream);
 
+/* Sparse-depth rasterisation on device (dataset.py:496-510, :316-329): d_tracks is (B,N,cols>=4) fp64
+   [id, x, y, z, ...] (np.loadtxt rows), d_counts (B) the valid rows per frame (NULL = N); the pixel is
+   (int(fc1*y/z + cc1), int(fc0*x/z + cc0)) in fp64 and, as in the reference's sequential loop, the LAST point on a pixel wins.
+   d_winner_ws: scratch of B*H*W int32; d_depth: (B,1,H,W) fp32 output. */
+int vidc_rasterize_sparse_depth(const double *d_tracks, const int32_t *d_counts, int32_t B, int32_t N, int32_t cols,
+                                double fc0, double fc1, double cc0, double cc1, int32_t H, int32_t W,
+                                int32_t *d_winner_ws, float *d_depth, void *stream);
+
 /* Replaces _build_homography (:35-58) plus the per-frame bbox / scale block (:125-140).
    d_Ig, d_Ia: (B,3) contiguous.  d_params: B entries. One thread per frame, no host sync. */
 int vidc_frame_params_compute(const vidc_camera *cam, const float *d_Ig, const float *d_Ia, int32_t B,

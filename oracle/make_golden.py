@@ -164,6 +164,43 @@ def backward_golden():
     return out
 
 
+def rasterize_golden():
+    """Row f2: the sparse-depth rasterisation block of the Demo loader (dataset.py:496-510), executed verbatim on synthetic
+    tracks (with pixel collisions and out-of-range points) and on the eight demo_dataset track files."""
+    import textwrap
+    import types
+    lines = open(os.path.join(REF_ROOT, "dataset.py")).read().splitlines()
+    block = textwrap.dedent("\n".join(lines[495:510]))           # 1-based lines 496..510
+    assert block.startswith("klt_depth_tensor = torch.zeros_like(color_tensor[0:1, :, :])") and block.rstrip().endswith("klt_tracks[i, 3]"), block
+    fake_self = types.SimpleNamespace(fc=np.array([202.9953, 202.9540]), cc=np.array([159.7645, 122.0951]))
+
+    def run(tracks):
+        loc = {"torch": torch, "np": np, "self": fake_self, "color_tensor": torch.zeros(3, 240, 320), "klt_tracks": tracks}
+        exec(block, loc)
+        return loc["klt_depth_tensor"].numpy().copy()
+
+    rs = np.random.RandomState(77)
+    frames = []
+    for n in (0, 1, 150, 400):
+        z = rs.rand(n) * 3.2 + 0.38
+        x = (rs.rand(n) * 2.2 - 1.1) * z
+        y = (rs.rand(n) * 1.7 - 0.85) * z
+        t = np.stack([np.arange(n, dtype=np.float64), x, y, z, rs.rand(n)], 1) if n else np.zeros((0, 5))
+        if n >= 150:                                              # force collisions: repeat a few points with other depths
+            t[10:20, 1:3] = t[0:10, 1:3] / t[0:10, 3:4] * t[10:20, 3:4]
+        frames.append(t)
+    ddir = os.path.join(REF_ROOT, "demo_dataset", "depth_sparse")
+    for f in sorted(os.listdir(ddir)):
+        frames.append(np.atleast_2d(np.loadtxt(os.path.join(ddir, f), delimiter=" ")))
+    N = max(t.shape[0] for t in frames)
+    tracks = np.zeros((len(frames), N, 5), np.float64); tracks[:, :, 3] = 1.0
+    counts = np.array([t.shape[0] for t in frames], np.int32)
+    for i, t in enumerate(frames):
+        tracks[i, :t.shape[0], :t.shape[1]] = t
+    depth = np.stack([run(t) for t in frames])
+    return {"tracks": tracks, "counts": counts, "fc": fake_self.fc, "cc": fake_self.cc, "depth": depth}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     # tiny: edge cases + random, everything in full
@@ -179,6 +216,7 @@ def main():
             I_g, I_a = np.concatenate([I_g, xg]), np.concatenate([I_a, xa])
         np.savez_compressed(os.path.join(OUT, f"golden_{name}.npz"), **run_reference(name, I_g, I_a, seed, full=False))
     np.savez_compressed(os.path.join(OUT, "golden_tiny_backward.npz"), **backward_golden())
+    np.savez_compressed(os.path.join(OUT, "golden_rasterize.npz"), **rasterize_golden())
     raw = gravity_cases()
     azure, scannet = reference_gravity_rules()
     ga = [azure(r) for r in raw]; gs = [scannet(r) for r in raw]

@@ -145,3 +145,15 @@ def test_cuda_backward_matches_reference_autograd(cuda_device):
     (torch.nn.functional.normalize(z2, dim=1) * wtt).sum().backward()      # torch's normalize backward on top of ours
     ref = g["grad_inverse_normals_normalized"]
     assert np.abs(n2.grad.cpu().numpy() - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+
+
+def test_cuda_sparse_depth_rasterisation_matches_reference(cuda_device):
+    """Row f2: point tracks -> (B,1,240,320) sparse depth on device, identical to the Demo loader's loop (dataset.py:496-510),
+    including pixel collisions (last point wins), out-of-range points, empty frames and the eight demo_dataset track files;
+    then warped (nearest, as is sensible for sparse samples) through the fused kernel."""
+    from vi_depth_completion_b200.gravity import rasterize_sparse_depth
+    g = np.load(os.path.join(GOLD, "golden_rasterize.npz"))
+    tracks = torch.from_numpy(g["tracks"]).to(cuda_device)
+    depth = rasterize_sparse_depth(tracks, g["counts"], g["fc"], g["cc"], 240, 320)
+    assert depth.shape == (tracks.shape[0], 1, 240, 320)
+    assert C.count_bit_mismatches(depth.cpu().numpy(), g["depth"]) == 0

@@ -26,3 +26,24 @@ def condition_gravity(raw_gravity: torch.Tensor, rule: str = "azure"):
     with torch.cuda.device(raw.device):
         check(lib().vidc_condition_gravity(raw.data_ptr(), B, RULES[rule], I_g.data_ptr(), I_a.data_ptr(), _stream_ptr(raw.device)))
     return I_g, I_a
+
+
+def rasterize_sparse_depth(tracks: torch.Tensor, counts, fc, cc, H: int, W: int):
+    """Row f2: (B,N,>=4) float64 KLT tracks [id, x, y, z, ...] -> (B,1,H,W) float32 sparse depth, as dataset.py:496-510 builds it
+    per sample on the host (pixel = int(fc * xy / z + cc) in fp64, last point on a pixel wins)."""
+    if not tracks.is_cuda or tracks.dtype != torch.float64 or tracks.dim() != 3 or tracks.shape[2] < 4:
+        raise RuntimeError("tracks: expected a (B,N,>=4) float64 CUDA tensor")
+    tr = tracks.contiguous()
+    B, N, cols = tr.shape
+    cnt = None
+    if counts is not None:
+        cnt = torch.as_tensor(counts, dtype=torch.int32, device=tr.device).contiguous()
+        if cnt.shape != (B,):
+            raise RuntimeError("counts: expected shape (B,)")
+    ws = torch.empty((B, H, W), dtype=torch.int32, device=tr.device)
+    depth = torch.empty((B, 1, H, W), dtype=torch.float32, device=tr.device)
+    with torch.cuda.device(tr.device):
+        check(lib().vidc_rasterize_sparse_depth(tr.data_ptr(), cnt.data_ptr() if cnt is not None else None, B, N, cols,
+                                                float(fc[0]), float(fc[1]), float(cc[0]), float(cc[1]), H, W,
+                                                ws.data_ptr(), depth.data_ptr(), _stream_ptr(tr.device)))
+    return depth
