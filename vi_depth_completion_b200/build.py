@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvidc_b200.so")
 SOURCES = [os.path.join(CSRC, "vidc_kernels.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("exact_math.cuh", "frame_params.cuh")] + [
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "vidc_b200.h")]
 
 NVCC_FLAGS = [

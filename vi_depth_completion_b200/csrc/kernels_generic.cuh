@@ -1,0 +1,296 @@
+// kernels_generic.cuh -- generic-stride kernels (any layout / size) and the small caller-side helpers
+// Part of libvidc_b200.so (one translation unit, vidc_kernels.cu); compiled with -fmad=false.
+#pragma once
+#include "device_common.cuh"
+
+namespace vidc_k {
+
+// ------------------------------------------------------------------------------------------
+// Forward warp.  MODE_A: interpolation of image A (C_A channels, 1..4); image D (1 channel, optional)
+// has its own mode.  ROT: rotate the 3 channels of A by R after sampling (:288, intent of :258-290).
+template <int C_A, bool HAS_D, bool ROT>
+__global__ void __launch_bounds__(256)
+warp_forward_kernel(const vidc_frame_params* __restrict__ prm, CamConst cam,
+                    ImgView a, ImgViewOut ya, int mode_a,
+                    ImgView d, ImgViewOut yd, int mode_d,
+                    unsigned char* __restrict__ mask, unsigned int* __restrict__ coverage) {
+    const int b = blockIdx.z;
+    const int X = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Y = blockIdx.y * blockDim.y + threadIdx.y;
+    const vidc_frame_params* __restrict__ P = prm + b;
+    float Hi[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Hi[k] = __ldg(&P->Hinv[k]);
+    const float px_min = __ldg(&P->px_min), py_min = __ldg(&P->py_min);
+    const float ikw = __ldg(&P->ikw), ikh = __ldg(&P->ikh);
+    const bool live = X < cam.W && Y < cam.H;
+    bool m = false;
+    if (live) {
+        float out_a[C_A];
+        {
+            float ix, iy;
+            forward_coords(Hi, px_min, py_min, ikw, ikh, cam, (float)X, (float)Y, (float)a.w, (float)a.h, ix, iy);
+            const float* __restrict__ base = a.p + (long long)b * a.sn;
+            if (mode_a == VIDC_BILINEAR) {
+                const Taps t = bilinear_taps(ix, iy, a.h, a.w, a.sh, a.sw);
+#pragma unroll
+                for (int c = 0; c < C_A; ++c) out_a[c] = sample_bilinear(base + c * a.sc, t);
+            } else {
+#pragma unroll
+                for (int c = 0; c < C_A; ++c) out_a[c] = sample_nearest(base + c * a.sc, ix, iy, a.h, a.w, a.sh, a.sw);
+            }
+        }
+        if (ROT && C_A == 3) {
+            float R[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) R[k] = __ldg(&P->R[k]);
+            float z[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) z[c] = fmaf(R[3 * c + 2], out_a[2], fmaf(R[3 * c + 1], out_a[1], R[3 * c] * out_a[0]));
+#pragma unroll
+            for (int c = 0; c < 3; ++c) out_a[c] = z[c];
+        }
+        float* __restrict__ ob = ya.p + (long long)b * ya.sn + Y * ya.sh + X * ya.sw;
+#pragma unroll
+        for (int c = 0; c < C_A; ++c) ob[c * ya.sc] = out_a[c];
+        if (C_A == 3) m = (out_a[0] + out_a[1]) + out_a[2] > 0.01f;       // surface_normal.py:151
+        if (HAS_D) {
+            float ix, iy;
+            forward_coords(Hi, px_min, py_min, ikw, ikh, cam, (float)X, (float)Y, (float)d.w, (float)d.h, ix, iy);
+            const float* __restrict__ base = d.p + (long long)b * d.sn;
+            float v;
+            if (mode_d == VIDC_BILINEAR) {
+                const Taps t = bilinear_taps(ix, iy, d.h, d.w, d.sh, d.sw);
+                v = sample_bilinear(base, t);
+            } else {
+                v = sample_nearest(base, ix, iy, d.h, d.w, d.sh, d.sw);
+            }
+            yd.p[(long long)b * yd.sn + Y * yd.sh + X * yd.sw] = v;
+        }
+        if (mask) mask[((long long)b * cam.H + Y) * cam.W + X] = m ? 1 : 0;
+    }
+    if (coverage) {   // warp-shuffle (ballot) reduction, then one shared and one global atomic per CTA
+        __shared__ unsigned int cta_count;
+        const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+        if (tid == 0) cta_count = 0;
+        __syncthreads();
+        const unsigned int bal = __ballot_sync(0xffffffffu, m);
+        if ((tid & 31) == 0 && bal) atomicAdd(&cta_count, __popc(bal));
+        __syncthreads();
+        if (tid == 0 && cta_count) atomicAdd(coverage + b, cta_count);
+    }
+}
+
+// Inverse warp of normals: gather + R^T rotation (+ F.normalize), ref :242-253, surface_normal.py:170
+template <bool NORMALIZE>
+__global__ void __launch_bounds__(256)
+unwarp_normals_kernel(const vidc_frame_params* __restrict__ prm, CamConst cam,
+                      ImgView x, ImgViewOut z, unsigned char* __restrict__ valid) {
+    const int b = blockIdx.z;
+    const int X = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (X >= cam.W || Y >= cam.H) return;
+    const vidc_frame_params* __restrict__ P = prm + b;
+    float Hm[9], R[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { Hm[k] = __ldg(&P->H[k]); R[k] = __ldg(&P->R[k]); }
+    const float px_min = __ldg(&P->px_min), py_min = __ldg(&P->py_min);
+    const float kw = __ldg(&P->kw), kh = __ldg(&P->kh);
+    float ix, iy;
+    inverse_coords(Hm, px_min, py_min, kw, kh, cam, (float)X, (float)Y, (float)x.w, (float)x.h, ix, iy);
+    const Taps t = bilinear_taps(ix, iy, x.h, x.w, x.sh, x.sw);
+    const float* __restrict__ base = x.p + (long long)b * x.sn;
+    const float y0 = sample_bilinear(base, t);
+    const float y1 = sample_bilinear(base + x.sc, t);
+    const float y2 = sample_bilinear(base + 2 * x.sc, t);
+    // z = C_R_Cg.bmm(y), C_R_Cg = R^T: z_c = sum_k R[k][c] y_k, k-ascending FMA chain (:253)
+    float z0 = fmaf(R[6], y2, fmaf(R[3], y1, R[0] * y0));
+    float z1 = fmaf(R[7], y2, fmaf(R[4], y1, R[1] * y0));
+    float z2 = fmaf(R[8], y2, fmaf(R[5], y1, R[2] * y0));
+    if (NORMALIZE) {   // z / max(||z||, 1e-12); squares summed left to right without FMA
+        const float n = fmaxf(sqrtf((z0 * z0 + z1 * z1) + z2 * z2), 1e-12f);
+        z0 = z0 / n; z1 = z1 / n; z2 = z2 / n;
+    }
+    float* __restrict__ ob = z.p + (long long)b * z.sn + Y * z.sh + X * z.sw;
+    ob[0] = z0; ob[z.sc] = z1; ob[2 * z.sc] = z2;
+    if (valid) valid[((long long)b * cam.H + Y) * cam.W + X] = (t.b_nw || t.b_ne || t.b_sw || t.b_se) ? 1 : 0;
+}
+
+// image_sampler_forward_inverse (:158-214): both grids, (B,H,W,2) contiguous, aspect guard :178-187
+__global__ void __launch_bounds__(256)
+sampler_grids_kernel(const vidc_frame_params* __restrict__ prm, CamConst cam,
+                     float2* __restrict__ grid, float2* __restrict__ inv_grid) {
+    const int b = blockIdx.z;
+    const int X = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (X >= cam.W || Y >= cam.H) return;
+    const vidc_frame_params* __restrict__ P = prm + b;
+    const float sigma = __ldg(&P->w_max) / __ldg(&P->h_max);              // :178
+    const bool guard = sigma < 0.8f || sigma > 2.2f;                       // :179
+    const long long o = ((long long)b * cam.H + Y) * cam.W + X;
+    const float Xf = (float)X, Yf = (float)Y;
+    float2 g, gi;
+    if (guard) {                                                           // :181-186
+        g.x = cam.inv_half_w * (Xf - cam.cx);
+        g.y = cam.inv_half_h * (Yf - cam.cy);
+        gi = g;
+    } else {
+        const float px_min = __ldg(&P->px_min), py_min = __ldg(&P->py_min);
+        {
+            const float* Hi = P->Hinv;
+            const float px = __ldg(&P->ikw) * Xf + px_min;
+            const float py = __ldg(&P->ikh) * Yf + py_min;
+            const float u = fmaf(__ldg(Hi + 1), py, __ldg(Hi + 0) * px) + __ldg(Hi + 2);
+            const float v = fmaf(__ldg(Hi + 4), py, __ldg(Hi + 3) * px) + __ldg(Hi + 5);
+            const float s = fmaf(__ldg(Hi + 7), py, __ldg(Hi + 6) * px) + __ldg(Hi + 8);
+            g.x = cam.inv_half_w * (u / s - cam.cx);
+            g.y = cam.inv_half_h * (v / s - cam.cy);
+        }
+        {
+            const float* Hm = P->H;
+            const float u = fmaf(__ldg(Hm + 1), Yf, __ldg(Hm + 0) * Xf) + __ldg(Hm + 2);
+            const float v = fmaf(__ldg(Hm + 4), Yf, __ldg(Hm + 3) * Xf) + __ldg(Hm + 5);
+            const float s = fmaf(__ldg(Hm + 7), Yf, __ldg(Hm + 6) * Xf) + __ldg(Hm + 8);
+            const float cxp = __ldg(&P->kw) * (u / s - px_min);
+            const float cyp = __ldg(&P->kh) * (v / s - py_min);
+            gi.x = cam.inv_half_w * (cxp - cam.cx);
+            gi.y = cam.inv_half_h * (cyp - cam.cy);
+        }
+    }
+    if (grid) grid[o] = g;
+    if (inv_grid) inv_grid[o] = gi;
+}
+
+__global__ void guard_rt_kernel(const vidc_frame_params* __restrict__ prm, int B, float* __restrict__ Rt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 9) return;
+    const int b = i / 9, k = i % 9;
+    const float sigma = prm[b].w_max / prm[b].h_max;
+    const bool guard = sigma < 0.8f || sigma > 2.2f;
+    Rt[i] = guard ? ((k % 4 == 0) ? 1.0f : 0.0f) : prm[b].R[3 * (k % 3) + k / 3];
+}
+
+// surface_normal.py:151 standalone
+__global__ void __launch_bounds__(256)
+validity_mask_kernel(ImgView x, unsigned char* __restrict__ mu8, float* __restrict__ mf32,
+                     unsigned int* __restrict__ coverage) {
+    const int b = blockIdx.z;
+    const int X = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Y = blockIdx.y * blockDim.y + threadIdx.y;
+    bool m = false;
+    if (X < x.w && Y < x.h) {
+        const float* __restrict__ p = x.p + (long long)b * x.sn + Y * x.sh + X * x.sw;
+        m = (__ldg(p) + __ldg(p + x.sc)) + __ldg(p + 2 * x.sc) > 0.01f;
+        const long long o = ((long long)b * x.h + Y) * x.w + X;
+        if (mu8) mu8[o] = m ? 1 : 0;
+        if (mf32) mf32[o] = m ? 1.0f : 0.0f;
+    }
+    if (coverage) {
+        __shared__ unsigned int cta_count;
+        const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+        if (tid == 0) cta_count = 0;
+        __syncthreads();
+        const unsigned int bal = __ballot_sync(0xffffffffu, m);
+        if ((tid & 31) == 0 && bal) atomicAdd(&cta_count, __popc(bal));
+        __syncthreads();
+        if (tid == 0 && cta_count) atomicAdd(coverage + b, cta_count);
+    }
+}
+
+// F.interpolate(mask, size, 'nearest'): src = min(floor(dst * (float)in / out), in - 1)
+__global__ void mask_nearest_kernel(const float* __restrict__ m, int B, int Hin, int Win, int Hout, int Wout,
+                                    float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * Hout * Wout;
+    if (i >= total) return;
+    const int x = (int)(i % Wout), y = (int)((i / Wout) % Hout), b = (int)(i / ((long long)Wout * Hout));
+    const float sh = (float)Hin / (float)Hout, sw = (float)Win / (float)Wout;
+    const int sy = min((int)floorf((float)y * sh), Hin - 1), sx = min((int)floorf((float)x * sw), Win - 1);
+    out[i] = __ldg(m + ((long long)b * Hin + sy) * Win + sx);
+}
+
+// all pyramid levels of surface_normal.py:153-156 in one launch (row f3); src u8 or f32 mask, f32 outputs
+struct PyramidArgs {
+    const unsigned char* m8; const float* m32;
+    int B, Hin, Win, levels;
+    int Ho[4], Wo[4];
+    long long begin[5];          // prefix sums of B*Ho*Wo
+    float* out[4];
+};
+__global__ void mask_pyramid_kernel(const __grid_constant__ PyramidArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.begin[a.levels]) return;
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) if (k < a.levels && i >= a.begin[k]) l = k;
+    const long long r = i - a.begin[l];
+    const int Ho = a.Ho[l], Wo = a.Wo[l];
+    const int x = (int)(r % Wo), y = (int)((r / Wo) % Ho), b = (int)(r / ((long long)Wo * Ho));
+    const float sh = (float)a.Hin / (float)Ho, sw = (float)a.Win / (float)Wo;
+    const int sy = min((int)floorf((float)y * sh), a.Hin - 1), sx = min((int)floorf((float)x * sw), a.Win - 1);
+    const long long src = ((long long)b * a.Hin + sy) * a.Win + sx;
+    a.out[l][r] = a.m8 ? (a.m8[src] ? 1.0f : 0.0f) : __ldg(a.m32 + src);
+}
+
+__global__ void __launch_bounds__(256) normalize3_kernel(ImgView z, ImgViewOut o) {
+    const int b = blockIdx.z;
+    const int X = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (X >= z.w || Y >= z.h) return;
+    const float* __restrict__ p = z.p + (long long)b * z.sn + Y * z.sh + X * z.sw;
+    const float z0 = __ldg(p), z1 = __ldg(p + z.sc), z2 = __ldg(p + 2 * z.sc);
+    const float n = fmaxf(sqrtf((z0 * z0 + z1 * z1) + z2 * z2), 1e-12f);
+    float* __restrict__ q = o.p + (long long)b * o.sn + Y * o.sh + X * o.sw;
+    q[0] = z0 / n; q[o.sc] = z1 / n; q[2 * o.sc] = z2 / n;
+}
+
+// normal_utils.py:7-34 in one pass; fp64 block reduction (warp shuffles), one atomic per CTA per stat
+__global__ void __launch_bounds__(256)
+normal_stats_kernel(ImgView gt, ImgView pred, ImgView mask, int normalize_prediction, double* __restrict__ out) {
+    const int b = blockIdx.z;
+    const int X = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Y = blockIdx.y * blockDim.y + threadIdx.y;
+    double s_ang = 0.0, s_m = 0.0, s_l1 = 0.0, s_cos = 0.0;
+    if (X < gt.w && Y < gt.h) {
+        const float* __restrict__ pp = pred.p + (long long)b * pred.sn + Y * pred.sh + X * pred.sw;
+        const float* __restrict__ pg = gt.p + (long long)b * gt.sn + Y * gt.sh + X * gt.sw;
+        const float m = __ldg(mask.p + (long long)b * mask.sn + Y * mask.sh + X * mask.sw);
+        const float r0 = __ldg(pp), r1 = __ldg(pp + pred.sc), r2 = __ldg(pp + 2 * pred.sc);
+        const float g0 = __ldg(pg), g1 = __ldg(pg + gt.sc), g2 = __ldg(pg + 2 * gt.sc);
+        float n0 = r0, n1 = r1, n2 = r2;
+        const float nr = sqrtf((r0 * r0 + r1 * r1) + r2 * r2);
+        if (normalize_prediction) {
+            const float nn = fmaxf(nr, 1e-12f);
+            n0 = r0 / nn; n1 = r1 / nn; n2 = r2 / nn;
+        }
+        float dp = (n0 * g0 + n1 * g1) + n2 * g2;
+        dp = fminf(fmaxf(dp, -1.0f), 1.0f);
+        const float ang = (float)((double)acosf(dp) / 3.14159265358979323846 * 180.0);
+        s_ang = (double)(ang * m);
+        s_m = (double)m;
+        s_l1 = fabs((double)(n0 * m) - (double)(g0 * m)) + fabs((double)(n1 * m) - (double)(g1 * m)) +
+               fabs((double)(n2 * m) - (double)(g2 * m));
+        // F.cosine_similarity(pred, gt, dim=1), eps = 1e-8 on each norm
+        const float ng = sqrtf((g0 * g0 + g1 * g1) + g2 * g2);
+        s_cos = (double)(((r0 * g0 + r1 * g1) + r2 * g2) / (fmaxf(nr, 1e-8f) * fmaxf(ng, 1e-8f)));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s_ang += __shfl_down_sync(0xffffffffu, s_ang, off);
+        s_m += __shfl_down_sync(0xffffffffu, s_m, off);
+        s_l1 += __shfl_down_sync(0xffffffffu, s_l1, off);
+        s_cos += __shfl_down_sync(0xffffffffu, s_cos, off);
+    }
+    __shared__ double sm[4][8];
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if ((tid & 31) == 0) { sm[0][tid >> 5] = s_ang; sm[1][tid >> 5] = s_m; sm[2][tid >> 5] = s_l1; sm[3][tid >> 5] = s_cos; }
+    __syncthreads();
+    if (tid < 4) {
+        double t = 0.0;
+        const int nw = (blockDim.x * blockDim.y + 31) >> 5;
+        for (int w = 0; w < nw; ++w) t += sm[tid][w];
+        if (t != 0.0) atomicAdd(out + tid, t);
+    }
+}
+
+}  // namespace vidc_k
