@@ -326,3 +326,41 @@ def test_cuda_graph_capture(cuda_device, oracle_mod):
     _, oz = o.inverse_warp_normal_image_with_gravity_center_aligned(normals, I_g, I_a)
     assert C.count_bit_mismatches(rgb_w.cpu().numpy(), oy) == 0
     assert C.count_bit_mismatches(nhat.cpu().numpy(), oracle_mod.normalize(oz)) == 0
+
+
+def test_forward_warp_of_normals_with_rotation(cuda_device, oracle_mod):
+    """a7, warp_normal_image_with_gravity_center_aligned (:258-290).  The reference method raises at :259, so parity is
+    against its evident intent: the forward warp of a4 (bit-exact, oracle) followed by z = R y (:288)."""
+    w, o = _mk("S1", cuda_device)
+    I_g, I_a = C.random_gravity(4, seed=41, roll_deg=50, pitch_deg=30)
+    normals = C.random_images(4, o.H, o.W, seed=2)[2]
+    for mode in ("bilinear", "nearest"):
+        H, z = w.warp_normal_image_with_gravity_center_aligned(_t(normals, cuda_device), _t(I_g, cuda_device), _t(I_a, cuda_device), interp_mode=mode)
+        oH, oy = o.warp_with_gravity_center_aligned(normals, I_g, I_a, interp_mode=mode)
+        _, R, _ = o.build_homography(I_g, I_a)
+        want = np.einsum("bck,bkhw->bchw", R.astype(np.float64), oy.astype(np.float64))
+        assert C.count_bit_mismatches(H.cpu().numpy(), oH) == 0
+        assert np.abs(z.cpu().numpy() - want).max() <= 2e-6
+
+
+def test_warp_with_explicit_homography(cuda_device, oracle_mod):
+    """a8, warp_with_homography (:292-310): dead code in the reference (numpy @ CUDA tensor).  Parity against a numpy fp64
+    restatement of those lines: bbox of the projected corners, NON-uniform kw / kh, inverse in fp64, grid, bilinear sample."""
+    w, o = _mk("S1", cuda_device)
+    W_, H_ = o.W, o.H
+    I_g, I_a = C.random_gravity(3, seed=19, roll_deg=25, pitch_deg=20)
+    Hm, _, _ = o.build_homography(I_g, I_a)
+    x = C.smooth_images(3, H_, W_, seed=5)
+    _, y = w.warp_with_homography(_t(x, cuda_device), torch.from_numpy(Hm))
+    cx, cy = C.CAMERAS["S1"][2], C.CAMERAS["S1"][3]
+    XX, YY = np.meshgrid(np.arange(W_, dtype=np.float64), np.arange(H_, dtype=np.float64))   # [row, col] layout directly
+    corners = np.array([[0, 0, 1], [W_ - 1, 0, 1], [0, H_ - 1, 1], [W_ - 1, H_ - 1, 1]], np.float64).T
+    for b in range(3):
+        Hb = Hm[b].astype(np.float64)
+        c = Hb @ corners; c /= c[2]
+        kw = W_ / (c[0].max() - c[0].min()); kh = H_ / (c[1].max() - c[1].min())           # :299-300
+        P = np.stack([XX / kw + c[0].min(), YY / kh + c[1].min(), np.ones_like(XX)]).reshape(3, -1)
+        q = np.linalg.inv(Hb) @ P; q /= q[2]
+        grid = np.stack([(q[0] - cx) / (W_ / 2), (q[1] - cy) / (H_ / 2)], -1).reshape(1, H_, W_, 2).astype(np.float32)
+        want = o.grid_sample(x[b:b + 1], grid)
+        assert np.abs(y[b:b + 1].cpu().numpy() - want).max() <= 1e-3

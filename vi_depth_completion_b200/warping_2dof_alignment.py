@@ -117,7 +117,6 @@ class Warping2DOFAlignment:
         self.H = np.int64(self._cam.H)
         self.device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
         self._const_cache = {}
-        self._ws = {}
 
     # ---- constant tensors the reference exposes as attributes (:15-24), built lazily ----------
     def _const(self, name):
@@ -148,14 +147,9 @@ class Warping2DOFAlignment:
     I3 = property(lambda self: self._const("I3"))
 
     def _params_ws(self, B, device):
-        key = (device, B)
-        ws = self._ws.get(key)
-        if ws is None:
-            if len(self._ws) > 8:
-                self._ws.clear()
-            ws = torch.empty((max(B, 1), _cabi.FRAME_PARAMS_FLOATS), dtype=torch.float32, device=device)
-            self._ws[key] = ws
-        return ws
+        """Scratch for B vidc_frame_params (192 B each).  Allocated per call from torch's stream-ordered caching allocator
+        (a microsecond), so concurrent use of one instance from several streams never shares scratch."""
+        return torch.empty((max(B, 1), _cabi.FRAME_PARAMS_FLOATS), dtype=torch.float32, device=device)
 
     def _skewsymm(self, x):  # :26-32, kept for API compatibility (pure tensor ops, no host sync)
         x = x.reshape(-1)
