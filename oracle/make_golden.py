@@ -8,6 +8,7 @@ What is frozen
   golden_tiny.npz   64x48 camera, 12 edge-case + 6 random frames: every intermediate and output IN FULL
                     (H, R, Hinv, both sampler grids, warped RGB, warped depth bilinear / nearest, un-normalised
                     and normalised un-warped normals, validity mask, nearest pyramid masks, loss statistics).
+  golden_tiny_special.npz  64x48, signed zeros / denormals / inf / NaN inputs: every output IN FULL
   golden_S1/S2/S3.npz  full-resolution configs of SURVEY.md section 8(d): parameters in full, and for the
                     large tensors a SHA-256 of the raw fp32 bytes plus 4096 sampled values (bit-exact check
                     without committing hundreds of MB).
@@ -201,6 +202,27 @@ def rasterize_golden():
     return {"tracks": tracks, "counts": counts, "fc": fake_self.fc, "cc": fake_self.cc, "depth": depth}
 
 
+def special_values_golden():
+    """Signed zeros, denormals, huge values, inf and NaN through the reference (tests/common.py: special_value_images):
+    the sign of a zero result, NaN propagation and the out-of-range behaviour of F.normalize, all outputs in full."""
+    Wref = load_reference_class("cpu")
+    fx, fy, cx, cy = C.CAMERAS["tiny"]
+    w = Wref(fx=fx, fy=fy, cx=cx, cy=cy)
+    B, Hh, Ww = 4, int(w.H), int(w.W)
+    rgb, depth, normals = C.special_value_images(B, Hh, Ww, seed=21)
+    I_g, I_a = C.special_value_gravity(B)
+    g, a = torch.from_numpy(I_g), torch.from_numpy(I_a)
+    with torch.no_grad():
+        _, y = w.warp_with_gravity_center_aligned(torch.from_numpy(rgb), g, a)
+        _, yd = w.warp_with_gravity_center_aligned(torch.from_numpy(depth), g, a)
+        _, ydn = w.warp_with_gravity_center_aligned(torch.from_numpy(depth), g, a, interp_mode="nearest")
+        _, z = w.inverse_warp_normal_image_with_gravity_center_aligned(torch.from_numpy(normals), g, a)
+        zn = F.normalize(z, dim=1)
+        mask = (y[:, 0:1] + y[:, 1:2] + y[:, 2:3] > 1e-2)
+    return {"B": np.int64(B), "seed": np.int64(21), "I_g": I_g, "I_a": I_a, "y_rgb": y.numpy(), "y_depth": yd.numpy(),
+            "y_depth_nearest": ydn.numpy(), "z": z.numpy(), "zn": zn.numpy(), "mask": mask.numpy().astype(np.uint8)}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     # tiny: edge cases + random, everything in full
@@ -217,6 +239,7 @@ def main():
         np.savez_compressed(os.path.join(OUT, f"golden_{name}.npz"), **run_reference(name, I_g, I_a, seed, full=False))
     np.savez_compressed(os.path.join(OUT, "golden_tiny_backward.npz"), **backward_golden())
     np.savez_compressed(os.path.join(OUT, "golden_rasterize.npz"), **rasterize_golden())
+    np.savez_compressed(os.path.join(OUT, "golden_tiny_special.npz"), **special_values_golden())
     raw = gravity_cases()
     azure, scannet = reference_gravity_rules()
     ga = [azure(r) for r in raw]; gs = [scannet(r) for r in raw]

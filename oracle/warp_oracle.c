@@ -316,11 +316,17 @@ API void vidc_oracle_grid_sample(const float *x, int B, int C, int Hin, int Win,
                     const int in_y0 = y0 >= 0 && y0 < Hin, in_y1 = y1 >= 0 && y1 < Hin;
                     for (int c = 0; c < C; ++c) {
                         const float *p = x + ((size_t)b * C + c) * Hin * Win;
-                        float acc = 0.0f;
-                        if (in_y0 && in_x0) acc = fmaf(p[(size_t)y0 * Win + x0], w_nw, acc);
-                        if (in_y0 && in_x1) acc = fmaf(p[(size_t)y0 * Win + x1], w_ne, acc);
-                        if (in_y1 && in_x0) acc = fmaf(p[(size_t)y1 * Win + x0], w_sw, acc);
-                        if (in_y1 && in_x1) acc = fmaf(p[(size_t)y1 * Win + x1], w_se, acc);
+                        /* ATen gathers 0 for an out-of-bounds tap and still runs it through the chain
+                           nw*w + ne*w + sw*w + se*w (first term a product, the rest contracted to FMAs): this
+                           decides the SIGN of a zero result (all-(-0) taps give -0, any padded tap gives +0) */
+                        const float v_nw = (in_y0 && in_x0) ? p[(size_t)y0 * Win + x0] : 0.0f;
+                        const float v_ne = (in_y0 && in_x1) ? p[(size_t)y0 * Win + x1] : 0.0f;
+                        const float v_sw = (in_y1 && in_x0) ? p[(size_t)y1 * Win + x0] : 0.0f;
+                        const float v_se = (in_y1 && in_x1) ? p[(size_t)y1 * Win + x1] : 0.0f;
+                        float acc = v_nw * w_nw;
+                        acc = fmaf(v_ne, w_ne, acc);
+                        acc = fmaf(v_sw, w_sw, acc);
+                        acc = fmaf(v_se, w_se, acc);
                         out[((size_t)b * C + c) * Hout * Wout + opix] = acc;
                     }
                 } else {
@@ -368,7 +374,7 @@ API void vidc_oracle_inverse_warp_normals(const oracle_camera *cam, const float 
         float *zb = z + 3 * hw * b;
         for (size_t p = 0; p < hw; ++p)
             for (int c = 0; c < 3; ++c) {
-                float s = R[c] * yb[p];
+                float s = fmaf(R[c], yb[p], 0.0f);   /* the GEMM accumulator starts at +0: I * (-0) = +0 */
                 s = fmaf(R[3 + c], yb[hw + p], s);
                 s = fmaf(R[6 + c], yb[2 * hw + p], s);
                 zb[c * hw + p] = s;

@@ -78,6 +78,47 @@ def random_images(B, H, W, seed, sparse_depth=False):
     return rgb, depth, normals
 
 
+SPECIAL_SCALES = np.array([0.0, 1e-42, 1e-35, 1e-31, 1e-25, 1e-19, 1e-15, 1e-9, 1.0, 1e9, 1e15, 1e19, 1e25, 1e35, np.inf],
+                          dtype=np.float32)
+
+
+def special_value_images(B, H, W, seed):
+    """Images that leave the comfortable range: signed zeros (x * 0 keeps the sign), denormals, huge values, inf and NaN,
+    in bands, per pixel and per component.  They pin the behaviour the random tests cannot see: the sign of a zero result
+    (ATen pads with +0 and MKL's GEMM accumulates from +0), NaN propagation through clamp_min, the IEEE fallbacks of the
+    reciprocal fast paths.  B >= 3."""
+    rgb, depth, normals = random_images(B, H, W, seed)
+    rs = np.random.RandomState(seed + 77)
+    sc = SPECIAL_SCALES
+    band = max(H // sc.size, 1)
+    with np.errstate(invalid="ignore", over="ignore"):
+        for i, s in enumerate(sc):                                           # frame 0: one magnitude per band of rows
+            normals[0, :, i * band:(i + 1) * band] *= s
+        normals[0, :, :band] *= np.float32(-1.0)                             # the zero band: mixed +-0
+        normals[0, :, :band, ::2] *= np.float32(-1.0)
+        normals[1] *= sc[rs.randint(0, sc.size, size=(H, W))][None]          # frame 1: per pixel ...
+        normals[1, 1] *= sc[rs.randint(0, sc.size, size=(H, W))]             # ... and per component
+        normals[2, 0, ::3] = 0.0                                             # frame 2: exact-zero components, some NaN
+        normals[2, 1, 1::5, ::2] = -0.0
+        normals[2, 2, 7::11, 3::4] = np.nan
+        rgb[0, :, : H // 3] *= np.float32(0.0)                               # +0 block (mask must be 0 there)
+        rgb[0, :, H // 3: H // 2] *= np.float32(-0.0)                        # -0 block
+        rgb[1, 0, 5::7, 2::5] = np.inf
+        rgb[1, 1, 3::9, 1::6] = np.nan
+        rgb[2] *= sc[rs.randint(5, 12, size=(H, W))][None]
+        depth[0, : H // 2] *= np.float32(-0.0)
+        depth[1, 4::6, 3::7] = np.nan
+        depth[2, 2::5, 1::4] = np.inf
+    return rgb, depth, normals
+
+
+def special_value_gravity(B, seed=8):
+    """Frame 0: gravity == alignment axis (R = I exactly, so exact zeros stay exact zeros); the rest moderate tilts."""
+    I_g, I_a = random_gravity(B, seed=seed, roll_deg=25, pitch_deg=25)
+    I_g[0], I_a[0] = (0.0, 1.0, 0.0), (0.0, 1.0, 0.0)
+    return I_g, I_a
+
+
 def smooth_images(B, H, W, seed):
     """Low-frequency images (real photographs are smooth): sums of a few sinusoids."""
     rs = np.random.RandomState(seed)

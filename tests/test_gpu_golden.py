@@ -157,3 +157,25 @@ def test_cuda_sparse_depth_rasterisation_matches_reference(cuda_device):
     depth = rasterize_sparse_depth(tracks, g["counts"], g["fc"], g["cc"], 240, 320)
     assert depth.shape == (tracks.shape[0], 1, 240, 320)
     assert C.count_bit_mismatches(depth.cpu().numpy(), g["depth"]) == 0
+
+
+def test_cuda_matches_reference_special_values(cuda_device):
+    """golden_tiny_special.npz: the executed reference on signed zeros / denormals / huge / inf / NaN inputs."""
+    from vi_depth_completion_b200.warping_2dof_alignment import Warping2DOFAlignment
+    g = np.load(os.path.join(GOLD, "golden_tiny_special.npz"))
+    fx, fy, cx, cy = C.CAMERAS["tiny"]
+    w = Warping2DOFAlignment(fx=fx, fy=fy, cx=cx, cy=cy)
+    B = int(g["B"])
+    rgb, depth, normals = C.special_value_images(B, int(w.H), int(w.W), int(g["seed"]))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    gg, aa = t(g["I_g"]), t(g["I_a"])
+    _, y = w.warp_with_gravity_center_aligned(t(rgb), gg, aa)
+    _, yd = w.warp_with_gravity_center_aligned(t(depth), gg, aa)
+    _, ydn = w.warp_with_gravity_center_aligned(t(depth), gg, aa, interp_mode="nearest")
+    _, z = w.inverse_warp_normal_image_with_gravity_center_aligned(t(normals), gg, aa)
+    _, zn = w.unwarp_normals(t(normals), gg, aa, normalize=True)
+    _, rgb_w, depth_w, mask = w.warp_rgbd(t(rgb), t(depth), gg, aa)
+    for got, key in ((y, "y_rgb"), (rgb_w, "y_rgb"), (yd, "y_depth"), (depth_w, "y_depth"), (ydn, "y_depth_nearest"),
+                     (z, "z"), (zn, "zn")):
+        assert C.count_bit_mismatches(got.cpu().numpy().reshape(g[key].shape), g[key]) == 0, key
+    assert np.array_equal(mask.cpu().numpy().reshape(-1), g["mask"].reshape(-1))

@@ -364,3 +364,39 @@ def test_warp_with_explicit_homography(cuda_device, oracle_mod):
         grid = np.stack([(q[0] - cx) / (W_ / 2), (q[1] - cy) / (H_ / 2)], -1).reshape(1, H_, W_, 2).astype(np.float32)
         want = o.grid_sample(x[b:b + 1], grid)
         assert np.abs(y[b:b + 1].cpu().numpy() - want).max() <= 1e-3
+
+
+
+@pytest.mark.parametrize("cam_name", ["S1", "tiny", "S2"])
+def test_special_values_match_oracle(cuda_device, oracle_mod, cam_name):
+    """Signed zeros, denormals, huge values, inf and NaN (tests/common.py: special_value_images).  The fused kernels take
+    reciprocal fast paths inside a magnitude window and IEEE sqrt / division outside it, pad with +0 taps and seed the
+    R^T product from +0: every output must land on the oracle's bits (the oracle is pinned on the same inputs against
+    the executed reference, tests/golden/golden_tiny_special.npz), at compile-time and runtime kernel geometries."""
+    from oracle import oracle as O
+    w, o = _mk(cam_name, cuda_device)
+    B, Hh, Ww = 4, int(w.H), int(w.W)
+    rgb, depth, normals = C.special_value_images(B, Hh, Ww, seed=21)
+    I_g, I_a = C.special_value_gravity(B)
+    g, a = _t(I_g, cuda_device), _t(I_a, cuda_device)
+    _, y = w.warp_with_gravity_center_aligned(_t(rgb, cuda_device), g, a)
+    _, ydn = w.warp_with_gravity_center_aligned(_t(depth, cuda_device), g, a, interp_mode="nearest")
+    _, rgb_w, depth_w, mask = w.warp_rgbd(_t(rgb, cuda_device), _t(depth, cuda_device), g, a)
+    _, z = w.inverse_warp_normal_image_with_gravity_center_aligned(_t(normals, cuda_device), g, a)
+    _, nhat = w.unwarp_normals(_t(normals, cuda_device), g, a)
+    from vi_depth_completion_b200 import normal_utils as NU
+    nhat2 = NU.Normalize(z)                                        # vidc_normalize3 (generic kernel)
+    with np.errstate(all="ignore"):
+        _, oy = o.warp_with_gravity_center_aligned(rgb, I_g, I_a)
+        _, oyd = o.warp_with_gravity_center_aligned(depth, I_g, I_a)
+        _, oydn = o.warp_with_gravity_center_aligned(depth, I_g, I_a, interp_mode="nearest")
+        _, oz = o.inverse_warp_normal_image_with_gravity_center_aligned(normals, I_g, I_a)
+        ozn = O.normalize(oz)
+    assert C.count_bit_mismatches(y.cpu().numpy(), oy) == 0
+    assert C.count_bit_mismatches(rgb_w.cpu().numpy(), oy) == 0
+    assert C.count_bit_mismatches(depth_w.cpu().numpy().reshape(oyd.shape), oyd) == 0
+    assert C.count_bit_mismatches(ydn.cpu().numpy().reshape(oydn.shape), oydn) == 0
+    assert np.array_equal(mask.cpu().numpy().reshape(-1), O.validity_mask(oy).reshape(-1))
+    assert C.count_bit_mismatches(z.cpu().numpy(), oz) == 0
+    assert C.count_bit_mismatches(nhat.cpu().numpy(), ozn) == 0
+    assert C.count_bit_mismatches(nhat2.cpu().numpy(), ozn) == 0

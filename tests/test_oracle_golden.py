@@ -101,3 +101,31 @@ def test_oracle_gravity_conditioning_matches_reference(oracle_mod, rule):
     Ig, Ia = oracle_mod.condition_gravity(g["raw"], rule)
     assert C.count_bit_mismatches(Ig, g[rule + "_g"]) == 0
     assert C.count_bit_mismatches(Ia, g[rule + "_a"]) == 0
+
+
+def test_oracle_matches_reference_special_values(oracle_mod):
+    """Signed zeros, denormals, huge values, inf, NaN (golden_tiny_special.npz, from the executed reference): the sign of a
+    zero result (+0 padding taps in grid_sample, +0 GEMM accumulator in bmm) and NaN propagation in F.normalize."""
+    g = _load("tiny_special")
+    fx, fy, cx, cy = C.CAMERAS["tiny"]
+    o = oracle_mod.Oracle(fx, fy, cx, cy)
+    B = int(g["B"])
+    rgb, depth, normals = C.special_value_images(B, o.H, o.W, int(g["seed"]))
+    I_g, I_a = C.special_value_gravity(B)
+    assert np.array_equal(I_g, g["I_g"]) and np.array_equal(I_a, g["I_a"])
+    with np.errstate(all="ignore"):
+        _, y = o.warp_with_gravity_center_aligned(rgb, I_g, I_a)
+        _, yd = o.warp_with_gravity_center_aligned(depth, I_g, I_a)
+        _, ydn = o.warp_with_gravity_center_aligned(depth, I_g, I_a, interp_mode="nearest")
+        _, z = o.inverse_warp_normal_image_with_gravity_center_aligned(normals, I_g, I_a)
+        zn = oracle_mod.normalize(z)
+    assert C.count_bit_mismatches(y, g["y_rgb"]) == 0
+    assert C.count_bit_mismatches(yd, g["y_depth"].reshape(yd.shape)) == 0
+    assert C.count_bit_mismatches(ydn, g["y_depth_nearest"].reshape(ydn.shape)) == 0
+    assert C.count_bit_mismatches(z, g["z"]) == 0
+    assert C.count_bit_mismatches(zn, g["zn"]) == 0
+    assert np.array_equal(oracle_mod.validity_mask(y), g["mask"].reshape(oracle_mod.validity_mask(y).shape))
+    # the cases are really in there: negative zeros survive the forward warp, none survive the GEMM, NaNs reach the output
+    assert (np.signbit(g["y_rgb"]) & (g["y_rgb"] == 0)).sum() > 100
+    assert (np.signbit(g["z"]) & (g["z"] == 0)).sum() == 0
+    assert np.isnan(g["zn"]).sum() > 100 and np.isnan(g["y_rgb"]).sum() > 10

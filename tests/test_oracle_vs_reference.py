@@ -77,3 +77,29 @@ def test_sin_restatement_matches_torch_sin(oracle_mod):
     out = np.empty_like(x)
     oracle_mod.lib().vidc_oracle_sinf_array(x.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(x.size), out.ctypes.data_as(ctypes.c_void_p))
     assert np.array_equal(out.view(np.uint32), torch.sin(torch.from_numpy(x)).numpy().view(np.uint32))
+
+
+def test_special_values_match_live_reference(oracle_mod):
+    """Signed zeros, denormals, inf, NaN at 320x240 against the executed reference (the 64x48 case is frozen as a golden)."""
+    import torch
+    from oracle.ref_loader import load_reference_class
+    warnings.filterwarnings("ignore")
+    Wref = load_reference_class("cpu")
+    fx, fy, cx, cy = C.CAMERAS["S1"]
+    w, o = Wref(fx=fx, fy=fy, cx=cx, cy=cy), oracle_mod.Oracle(fx, fy, cx, cy)
+    rgb, depth, normals = C.special_value_images(4, o.H, o.W, seed=21)
+    I_g, I_a = C.special_value_gravity(4)
+    g, a = torch.from_numpy(I_g), torch.from_numpy(I_a)
+    with np.errstate(all="ignore"):
+        _, y = w.warp_with_gravity_center_aligned(torch.from_numpy(rgb), g, a)
+        _, ydn = w.warp_with_gravity_center_aligned(torch.from_numpy(depth), g, a, interp_mode="nearest")
+        _, z = w.inverse_warp_normal_image_with_gravity_center_aligned(torch.from_numpy(normals), g, a)
+        zn = torch.nn.functional.normalize(z, dim=1)
+        _, oy = o.warp_with_gravity_center_aligned(rgb, I_g, I_a)
+        _, oydn = o.warp_with_gravity_center_aligned(depth, I_g, I_a, interp_mode="nearest")
+        _, oz = o.inverse_warp_normal_image_with_gravity_center_aligned(normals, I_g, I_a)
+        ozn = oracle_mod.normalize(oz)
+    assert C.count_bit_mismatches(y.numpy(), oy) == 0
+    assert C.count_bit_mismatches(ydn.numpy().reshape(oydn.shape), oydn) == 0
+    assert C.count_bit_mismatches(z.numpy(), oz) == 0
+    assert C.count_bit_mismatches(zn.numpy(), ozn) == 0

@@ -36,9 +36,9 @@ warp_backward_kernel(const vidc_frame_params* __restrict__ prm, CamConst cam, Im
 #pragma unroll
         for (int k = 0; k < 9; ++k) R[k] = __ldg(&P->R[k]);
         const float a0 = gv[0], a1 = gv[1], a2 = gv[2];
-        gv[0] = fmaf(R[2], a2, fmaf(R[1], a1, R[0] * a0));
-        gv[1] = fmaf(R[5], a2, fmaf(R[4], a1, R[3] * a0));
-        gv[2] = fmaf(R[8], a2, fmaf(R[7], a1, R[6] * a0));
+        gv[0] = fmaf(R[2], a2, fmaf(R[1], a1, fmaf(R[0], a0, 0.0f)));
+        gv[1] = fmaf(R[5], a2, fmaf(R[4], a1, fmaf(R[3], a0, 0.0f)));
+        gv[2] = fmaf(R[8], a2, fmaf(R[7], a1, fmaf(R[6], a0, 0.0f)));
     }
     float* __restrict__ out = gx + (long long)b * gx_sn;
     if (mode == VIDC_BILINEAR) {

@@ -46,7 +46,7 @@ warp_forward_kernel(const vidc_frame_params* __restrict__ prm, CamConst cam,
             for (int k = 0; k < 9; ++k) R[k] = __ldg(&P->R[k]);
             float z[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) z[c] = fmaf(R[3 * c + 2], out_a[2], fmaf(R[3 * c + 1], out_a[1], R[3 * c] * out_a[0]));
+            for (int c = 0; c < 3; ++c) z[c] = fmaf(R[3 * c + 2], out_a[2], fmaf(R[3 * c + 1], out_a[1], fmaf(R[3 * c], out_a[0], 0.0f)));
 #pragma unroll
             for (int c = 0; c < 3; ++c) out_a[c] = z[c];
         }
@@ -103,12 +103,13 @@ unwarp_normals_kernel(const vidc_frame_params* __restrict__ prm, CamConst cam,
     const float y0 = sample_bilinear(base, t);
     const float y1 = sample_bilinear(base + x.sc, t);
     const float y2 = sample_bilinear(base + 2 * x.sc, t);
-    // z = C_R_Cg.bmm(y), C_R_Cg = R^T: z_c = sum_k R[k][c] y_k, k-ascending FMA chain (:253)
-    float z0 = fmaf(R[6], y2, fmaf(R[3], y1, R[0] * y0));
-    float z1 = fmaf(R[7], y2, fmaf(R[4], y1, R[1] * y0));
-    float z2 = fmaf(R[8], y2, fmaf(R[5], y1, R[2] * y0));
+    // z = C_R_Cg.bmm(y), C_R_Cg = R^T: z_c = sum_k R[k][c] y_k, k-ascending FMA chain from a +0
+    // accumulator like the GEMM behind bmm (:253) -- the seed decides the sign of a zero result: I * (-0) = +0
+    float z0 = fmaf(R[6], y2, fmaf(R[3], y1, fmaf(R[0], y0, 0.0f)));
+    float z1 = fmaf(R[7], y2, fmaf(R[4], y1, fmaf(R[1], y0, 0.0f)));
+    float z2 = fmaf(R[8], y2, fmaf(R[5], y1, fmaf(R[2], y0, 0.0f)));
     if (NORMALIZE) {   // z / max(||z||, 1e-12); squares summed left to right without FMA
-        const float n = fmaxf(sqrtf((z0 * z0 + z1 * z1) + z2 * z2), 1e-12f);
+        const float n = clamp_min_eps(sqrtf((z0 * z0 + z1 * z1) + z2 * z2));
         z0 = z0 / n; z1 = z1 / n; z2 = z2 / n;
     }
     float* __restrict__ ob = z.p + (long long)b * z.sn + Y * z.sh + X * z.sw;
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(256) normalize3_kernel(ImgView z, ImgViewOut o
     if (X >= z.w || Y >= z.h) return;
     const float* __restrict__ p = z.p + (long long)b * z.sn + Y * z.sh + X * z.sw;
     const float z0 = __ldg(p), z1 = __ldg(p + z.sc), z2 = __ldg(p + 2 * z.sc);
-    const float n = fmaxf(sqrtf((z0 * z0 + z1 * z1) + z2 * z2), 1e-12f);
+    const float n = clamp_min_eps(sqrtf((z0 * z0 + z1 * z1) + z2 * z2));
     float* __restrict__ q = o.p + (long long)b * o.sn + Y * o.sh + X * o.sw;
     q[0] = z0 / n; q[o.sc] = z1 / n; q[2 * o.sc] = z2 / n;
 }
@@ -260,11 +261,12 @@ normal_stats_kernel(ImgView gt, ImgView pred, ImgView mask, int normalize_predic
         float n0 = r0, n1 = r1, n2 = r2;
         const float nr = sqrtf((r0 * r0 + r1 * r1) + r2 * r2);
         if (normalize_prediction) {
-            const float nn = fmaxf(nr, 1e-12f);
+            const float nn = clamp_min_eps(nr);
             n0 = r0 / nn; n1 = r1 / nn; n2 = r2 / nn;
         }
         float dp = (n0 * g0 + n1 * g1) + n2 * g2;
-        dp = fminf(fmaxf(dp, -1.0f), 1.0f);
+        dp = dp < -1.0f ? -1.0f : dp;                      // torch.clamp keeps NaN (normal_utils.py:12)
+        dp = dp > 1.0f ? 1.0f : dp;
         const float ang = (float)((double)acosf(dp) / 3.14159265358979323846 * 180.0);
         s_ang = (double)(ang * m);
         s_m = (double)m;

@@ -311,11 +311,11 @@ unwarp_normals_tma_kernel(const __grid_constant__ InvArgs a, const __grid_consta
             } else {
                 y = inv_sample_row(in, x_sh, x_sc, H, W, tp);
             }
-            float z0 = fmaf(R[6], y.c, fmaf(R[3], y.b, R[0] * y.a));
-            float z1 = fmaf(R[7], y.c, fmaf(R[4], y.b, R[1] * y.a));
-            float z2 = fmaf(R[8], y.c, fmaf(R[5], y.b, R[2] * y.a));
+            float z0 = fmaf(R[6], y.c, fmaf(R[3], y.b, fmaf(R[0], y.a, 0.0f)));
+            float z1 = fmaf(R[7], y.c, fmaf(R[4], y.b, fmaf(R[1], y.a, 0.0f)));
+            float z2 = fmaf(R[8], y.c, fmaf(R[5], y.b, fmaf(R[2], y.a, 0.0f)));
             if (NORMALIZE) {
-                const float n = fmaxf(sqrtf((z0 * z0 + z1 * z1) + z2 * z2), 1e-12f);
+                const float n = clamp_min_eps(sqrtf((z0 * z0 + z1 * z1) + z2 * z2));
                 div3_rn(z0, z1, z2, n);
             }
             if (live) {
