@@ -26,6 +26,11 @@
  * tests/golden/ made by oracle/make_golden.py.  Every float operation below is a
  * separately rounded IEEE binary32 op unless written as fmaf(); compile with
  * -ffp-contract=off (see oracle/Makefile).
+ *
+ * One documented divergence from the CPU-executed reference: a NON-FINITE sampling
+ * coordinate (non-finite gravity input only) reads as out of bounds here, as in the CUDA
+ * build of ATen (GridSampler.cuh:140-147) -- the CPU build returns NaN in bilinear mode.
+ * tests/test_oracle_vs_reference.py::test_degenerate_gravity_against_live_reference.
  */
 #include <math.h>
 #include <pthread.h>

@@ -119,6 +119,18 @@ def special_value_gravity(B, seed=8):
     return I_g, I_a
 
 
+def degenerate_gravity():
+    """Gravity / alignment vectors no IMU should produce: zero, NaN, inf, overflowing and underflowing magnitudes, signed
+    zeros.  The parameter chain (atan2, cos, the bbox min / max) must still follow the reference bit for bit; frames whose
+    homography is non-finite have non-finite sampling grids."""
+    g = np.array([[0, 0, 0], [np.nan, 1, 0], [0, np.inf, 0], [1e30, 1e30, 0], [1e-30, 1e-30, 1e-30], [0, 1e-45, 0],
+                  [3e38, 3e38, 3e38], [0, 1, 0], [0, 1, 0], [0, 1, 0], [-0.0, 1, -0.0], [0, 1, 1e-20], [1e-20, 1, 0],
+                  [0.1, -np.inf, 0.2], [1e19, 1e19, 1e19], [1e-23, 1e-23, 1e-23]], np.float32)
+    a = np.tile(np.array([[0, 1, 0]], np.float32), (g.shape[0], 1))
+    a[7] = [0, 0, 0]; a[8] = [np.nan, 0, 1]; a[9] = [0, 1e20, 0]
+    return g, a
+
+
 def smooth_images(B, H, W, seed):
     """Low-frequency images (real photographs are smooth): sums of a few sinusoids."""
     rs = np.random.RandomState(seed)

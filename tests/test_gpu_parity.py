@@ -400,3 +400,36 @@ def test_special_values_match_oracle(cuda_device, oracle_mod, cam_name):
     assert C.count_bit_mismatches(z.cpu().numpy(), oz) == 0
     assert C.count_bit_mismatches(nhat.cpu().numpy(), ozn) == 0
     assert C.count_bit_mismatches(nhat2.cpu().numpy(), ozn) == 0
+
+
+def test_degenerate_gravity_matches_oracle(cuda_device, oracle_mod):
+    """Zero / NaN / inf / overflowing gravity: parameters, grids and every output on the oracle's bits.  Non-finite
+    sampling coordinates read as out of bounds (ATen's CUDA safe_downgrade_to_int_range, GridSampler.cuh:140-147): zeros."""
+    from oracle import oracle as O
+    for cam_name in ("tiny", "S1"):
+        w, o = _mk(cam_name, cuda_device)
+        I_g, I_a = C.degenerate_gravity()
+        B, Hh, Ww = I_g.shape[0], int(w.H), int(w.W)
+        g, a = _t(I_g, cuda_device), _t(I_a, cuda_device)
+        with np.errstate(all="ignore"):
+            _check_params(w, o, I_g, I_a, cuda_device)
+            rgb, depth, normals = C.random_images(B, Hh, Ww, seed=3)
+            Rt, grid, inv = w.image_sampler_forward_inverse(g, a)
+            oRt, ogrid, oinv = o.image_sampler_forward_inverse(I_g, I_a)
+            _, rgb_w, depth_w, mask = w.warp_rgbd(_t(rgb, cuda_device), _t(depth, cuda_device), g, a)
+            _, y = w.warp_with_gravity_center_aligned(_t(rgb, cuda_device), g, a)
+            _, z = w.inverse_warp_normal_image_with_gravity_center_aligned(_t(normals, cuda_device), g, a)
+            _, nhat = w.unwarp_normals(_t(normals, cuda_device), g, a)
+            _, oy = o.warp_with_gravity_center_aligned(rgb, I_g, I_a)
+            _, oyd = o.warp_with_gravity_center_aligned(depth, I_g, I_a)
+            _, oz = o.inverse_warp_normal_image_with_gravity_center_aligned(normals, I_g, I_a)
+            ozn = O.normalize(oz)
+        assert C.count_bit_mismatches(Rt.cpu().numpy(), oRt) == 0
+        assert C.count_bit_mismatches(grid.cpu().numpy(), ogrid) == 0
+        assert C.count_bit_mismatches(inv.cpu().numpy(), oinv) == 0
+        assert C.count_bit_mismatches(y.cpu().numpy(), oy) == 0
+        assert C.count_bit_mismatches(rgb_w.cpu().numpy(), oy) == 0
+        assert C.count_bit_mismatches(depth_w.cpu().numpy().reshape(oyd.shape), oyd) == 0
+        assert np.array_equal(mask.cpu().numpy().reshape(-1), O.validity_mask(oy).reshape(-1))
+        assert C.count_bit_mismatches(z.cpu().numpy(), oz) == 0
+        assert C.count_bit_mismatches(nhat.cpu().numpy(), ozn) == 0

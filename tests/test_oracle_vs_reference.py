@@ -103,3 +103,41 @@ def test_special_values_match_live_reference(oracle_mod):
     assert C.count_bit_mismatches(ydn.numpy().reshape(oydn.shape), oydn) == 0
     assert C.count_bit_mismatches(z.numpy(), oz) == 0
     assert C.count_bit_mismatches(zn.numpy(), ozn) == 0
+
+
+def test_degenerate_gravity_against_live_reference(oracle_mod):
+    """Zero / NaN / inf / overflowing gravity.  Parameters and sampling grids equal the executed reference bit for bit.
+    Outputs equal it wherever the frame's sampling coordinates are finite.  KNOWN, DOCUMENTED divergence: for a
+    non-finite coordinate the CPU build of ATen returns NaN in bilinear mode (0 * NaN weights) while its CUDA build -- the
+    reference's deployment device -- returns 0 (safe_downgrade_to_int_range, GridSampler.cuh:140-147); the oracle and the
+    kernels follow the CUDA build."""
+    import torch
+    from oracle.ref_loader import load_reference_class
+    warnings.filterwarnings("ignore")
+    Wref = load_reference_class("cpu")
+    fx, fy, cx, cy = C.CAMERAS["tiny"]
+    w, o = Wref(fx=fx, fy=fy, cx=cx, cy=cy), oracle_mod.Oracle(fx, fy, cx, cy)
+    I_g, I_a = C.degenerate_gravity()
+    B = I_g.shape[0]
+    rgb, depth, normals = C.random_images(B, o.H, o.W, seed=3)
+    g, a = torch.from_numpy(I_g), torch.from_numpy(I_a)
+    with np.errstate(all="ignore"):
+        H, R, Hi = w._build_homography(g, a)
+        Rt, grid, inv = w.image_sampler_forward_inverse(g, a)
+        _, y = w.warp_with_gravity_center_aligned(torch.from_numpy(rgb), g, a)
+        _, ydn = w.warp_with_gravity_center_aligned(torch.from_numpy(depth), g, a, interp_mode="nearest")
+        _, z = w.inverse_warp_normal_image_with_gravity_center_aligned(torch.from_numpy(normals), g, a)
+        oH, oR, oHi = o.build_homography(I_g, I_a)
+        oRt, ogrid, oinv = o.image_sampler_forward_inverse(I_g, I_a)
+        _, oy = o.warp_with_gravity_center_aligned(rgb, I_g, I_a)
+        _, oydn = o.warp_with_gravity_center_aligned(depth, I_g, I_a, interp_mode="nearest")
+        _, oz = o.inverse_warp_normal_image_with_gravity_center_aligned(normals, I_g, I_a)
+    for got, want in ((R, oR), (H, oH), (Hi, oHi), (Rt, oRt), (grid, ogrid), (inv, oinv)):
+        assert C.count_bit_mismatches(got.numpy(), want) == 0
+    assert C.count_bit_mismatches(ydn.numpy().reshape(oydn.shape), oydn) == 0      # nearest: 0 on both builds
+    fwd_finite = np.isfinite(ogrid).all(axis=(1, 2, 3))
+    inv_finite = np.isfinite(oinv).all(axis=(1, 2, 3))
+    assert 3 <= (~fwd_finite).sum() < B
+    assert C.count_bit_mismatches(y.numpy()[fwd_finite], oy[fwd_finite]) == 0
+    assert C.count_bit_mismatches(z.numpy()[inv_finite], oz[inv_finite]) == 0
+    assert np.isnan(y.numpy()[~fwd_finite]).all() and (oy[~fwd_finite] == 0).all()  # the divergence, exactly as documented
