@@ -180,6 +180,13 @@ def test_errors(cuda_device):
         w.warp_with_gravity_center_aligned(torch.zeros(2, 3, 240, 320), g, g)          # CPU tensor: no fallback
     with pytest.raises(RuntimeError):
         w.inverse_warp_normal_image_with_gravity_center_aligned(torch.zeros(2, 3, 100, 100, device=cuda_device), g, g)
+    img = torch.zeros(2, 3, 240, 320, device=cuda_device)
+    with pytest.raises(ValueError, match="expected mode to be"):        # F.grid_sample's own check (reference :150)
+        w.warp_with_gravity_center_aligned(img, g, g, interp_mode="cubic")
+    with pytest.raises(ValueError):
+        w.warp_rgbd(img, img[:, 0], g, g, depth_mode="linear")
+    with pytest.raises(NotImplementedError):                            # valid in torch, never used by the reference
+        w.warp_with_gravity_center_aligned(img, g, g, interp_mode="bicubic")
     x = torch.zeros(2, 3, 240, 320, device=cuda_device, requires_grad=True)
     _, y = w.unwarp_normals(x, g, g)                        # fused renormalising entry point: forward-only
     with pytest.raises(NotImplementedError):

@@ -104,6 +104,19 @@ def _attach(x, out, warper=None, g=None, a=None, inverse=False, mode=0):
     return out
 
 
+def _check_interp_mode(interp_mode):
+    """F.grid_sample's own check (the reference forwards interp_mode to it, :150): ValueError for an unknown mode.
+    'bicubic' is valid there but never used by the reference's callers (surface_normal.py:148-169 pass 'bilinear' /
+    'nearest'); it is not implemented here and says so instead of silently sampling differently."""
+    if interp_mode in ("bilinear", "nearest"):
+        return
+    if interp_mode == "bicubic":
+        raise NotImplementedError("interp_mode='bicubic' is not implemented by the B200 path (the reference only calls "
+                                  "'bilinear' and 'nearest')")
+    raise ValueError("nn.functional.grid_sample(): expected mode to be 'bilinear', 'nearest' or 'bicubic', "
+                     f"but got: '{interp_mode}'")
+
+
 class Warping2DOFAlignment:
     # networks/warping_2dof_alignment.py:6
     def __init__(self, fx=577.87061 * 0.5, fy=577.87061 * 0.5, cx=319.87654 * 0.5, cy=239.87603 * 0.5):
@@ -195,8 +208,7 @@ class Warping2DOFAlignment:
             flag_fix_return = True
         if x.dim() != 4:
             raise RuntimeError(f"x: expected a 3-D or 4-D tensor, got {x.dim()}-D")
-        if interp_mode not in ("bilinear", "nearest"):
-            raise RuntimeError(f"interp_mode must be 'bilinear' or 'nearest', got {interp_mode!r}")
+        _check_interp_mode(interp_mode)
         device = x.device
         g, a = _gravity(I_g, I_a, device)
         y = self._empty_like_canvas(x)
@@ -255,8 +267,7 @@ class Warping2DOFAlignment:
         _require_cuda_f32(x, "x")
         if x.dim() != 4 or x.shape[1] != 3:
             raise RuntimeError("x: expected (B,3,H,W)")
-        if interp_mode not in ("bilinear", "nearest"):
-            raise RuntimeError(f"interp_mode must be 'bilinear' or 'nearest', got {interp_mode!r}")
+        _check_interp_mode(interp_mode)
         device = x.device
         g, a = _gravity(I_g, I_a, device)
         z = self._empty_like_canvas(x)
@@ -293,6 +304,7 @@ class Warping2DOFAlignment:
     def warp_rgbd(self, x_rgb, x_depth, I_g, I_a, depth_mode='bilinear', with_mask=True, with_coverage=False):
         """One pass: warp RGB (B,3,h,w) and sparse depth (B,h,w)/(B,1,h,w) into the gravity-aligned canvas and
         emit the validity mask of surface_normal.py:151.  Returns (Cg_H_C, rgb_w, depth_w, mask_u8[, coverage])."""
+        _check_interp_mode(depth_mode)
         _require_cuda_f32(x_rgb, "x_rgb")
         device = x_rgb.device
         g, a = _gravity(I_g, I_a, device)
@@ -328,6 +340,7 @@ class Warping2DOFAlignment:
     def warp_rgbd_packed(self, x_rgbd, I_g, I_a, depth_mode='bilinear', with_mask=True, with_coverage=False):
         """Packed RGBD forward warp: x_rgbd is (B,4,h,w) in channels-last memory format (R,G,B,depth interleaved, 16 B per
         pixel), so each bilinear tap is one 128-bit load.  Returns (Cg_H_C, y_rgbd channels-last, mask_u8[, coverage])."""
+        _check_interp_mode(depth_mode)
         _require_cuda_f32(x_rgbd, "x_rgbd")
         if x_rgbd.dim() != 4 or x_rgbd.shape[1] != 4 or not x_rgbd.is_contiguous(memory_format=torch.channels_last):
             raise RuntimeError("x_rgbd: expected a (B,4,H,W) tensor in torch.channels_last memory format")
