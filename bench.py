@@ -296,7 +296,11 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_peak()
         px = B * H * W
-        dom = ("warp_rgbd_fast_kernel", fwd_ms, BYTES_PER_PX_FWD) if fwd_ms >= inv_ms else ("unwarp_normals_fast_kernel", inv_ms, BYTES_PER_PX_INV)
+        # kernel families behind the fused entry points (vidc_kernels.cu: shear_level(), VIDC_SHEAR, default 1)
+        shear = os.environ.get("VIDC_SHEAR", "1")[:1]
+        fwd_name = "warp_rgbd_fast_kernel" if shear == "0" else "warp_rgbd_shear_kernel"
+        inv_name = "unwarp_normals_shear_kernel" if shear == "2" else "unwarp_normals_fast_kernel"
+        dom = (fwd_name, fwd_ms, BYTES_PER_PX_FWD) if fwd_ms >= inv_ms else (inv_name, inv_ms, BYTES_PER_PX_INV)
         achieved = px * dom[2] / (dom[1] * 1e-3) / 1e9
         traffic = ncu_traffic()
         roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -304,8 +308,8 @@ def run_ours(args):
                     "traffic": ((traffic or {}).get(dom[0]) or {}).get("dram_bytes_total"),
                     "traffic_source": ((traffic or {}).get(dom[0]) or {}).get("source"),
                     "algorithmic_bytes_per_launch": px * dom[2],
-                    "kernels": {"warp_rgbd_fast_kernel": {"ms": fwd_ms, "GBps": px * BYTES_PER_PX_FWD / fwd_ms / 1e6},
-                                "unwarp_normals_fast_kernel": {"ms": inv_ms, "GBps": px * BYTES_PER_PX_INV / inv_ms / 1e6},
+                    "kernels": {fwd_name: {"ms": fwd_ms, "GBps": px * BYTES_PER_PX_FWD / fwd_ms / 1e6},
+                                inv_name: {"ms": inv_ms, "GBps": px * BYTES_PER_PX_INV / inv_ms / 1e6},
                                 "warp_rgbd_nhwc4_kernel (opt-in packed RGBD layout, not part of `value`)": {
                                     "ms": packed_ms, "GBps": px * BYTES_PER_PX_FWD / packed_ms / 1e6,
                                     "frac": px * BYTES_PER_PX_FWD / packed_ms / 1e6 / peak}},

@@ -200,43 +200,69 @@ def test_empty_batch(cuda_device):
     assert y.shape == (0, 3, 240, 320) and H.shape == (0, 3, 3)
 
 
-def test_tma_staged_forward_kernel_matches_oracle(cuda_device, oracle_mod):
-    """The opt-in TMA-staged forward kernel (VIDC_TMA=1, cp.async.bulk.tensor footprint staging) in a fresh process:
-    same bits as the oracle, including tiles that fall back (extreme roll) and exterior tiles."""
-    import os
-    import subprocess
-    import sys
-    code = r'''
+_VARIANT_CODE = r'''
 import sys, numpy as np, torch
 sys.path.insert(0, %r)
 from tests import common as C
 from oracle import oracle as O
 from vi_depth_completion_b200.warping_2dof_alignment import Warping2DOFAlignment
 dev = torch.device("cuda", 0)
+t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 for cam, (I_g, I_a) in (("S1", C.random_gravity(6, 1234)), ("S2", C.random_gravity(3, 77)), ("S3", C.extreme_roll_gravity(7, 3)),
-                        ("tiny", C.edge_case_gravity())):
+                        ("S1", C.random_gravity(5, 9, roll_deg=70, pitch_deg=40)), ("tiny", C.edge_case_gravity()),
+                        ("S1", C.edge_case_gravity())):
     w, o = Warping2DOFAlignment(*C.CAMERAS[cam]), O.Oracle(*C.CAMERAS[cam])
     B = I_g.shape[0]
     rgb, depth, _ = C.random_images(B, o.H, o.W, 5)
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     for mode in ("bilinear", "nearest"):
-        _, rgb_w, depth_w, mask = w.warp_rgbd(t(rgb), t(depth), t(I_g), t(I_a), depth_mode=mode)
+        _, rgb_w, depth_w, mask, cov = w.warp_rgbd(t(rgb), t(depth), t(I_g), t(I_a), depth_mode=mode, with_coverage=True)
         _, oy = o.warp_with_gravity_center_aligned(rgb, I_g, I_a)
         _, od = o.warp_with_gravity_center_aligned(depth, I_g, I_a, interp_mode=mode)
+        om = O.validity_mask(oy)
         assert C.count_bit_mismatches(rgb_w.cpu().numpy(), oy) == 0, (cam, mode, "rgb")
         assert C.count_bit_mismatches(depth_w.cpu().numpy(), od) == 0, (cam, mode, "depth")
-        assert np.array_equal(mask.cpu().numpy(), O.validity_mask(oy)), (cam, mode, "mask")
+        assert np.array_equal(mask.cpu().numpy(), om), (cam, mode, "mask")
+        assert np.array_equal(cov.cpu().numpy().astype(np.int64), om.reshape(B, -1).sum(1).astype(np.int64)), (cam, mode, "coverage")
+    _, rgb_only, _, mask_only = w.warp_rgbd(t(rgb), None, t(I_g), t(I_a))
+    assert C.count_bit_mismatches(rgb_only.cpu().numpy(), oy) == 0 and np.array_equal(mask_only.cpu().numpy(), om), (cam, "rgb only")
     nrm = C.random_images(B, o.H, o.W, 6)[2]
     _, z = w.inverse_warp_normal_image_with_gravity_center_aligned(t(nrm), t(I_g), t(I_a))
     _, nh, valid = w.unwarp_normals(t(nrm), t(I_g), t(I_a), with_valid=True)
     _, oz = o.inverse_warp_normal_image_with_gravity_center_aligned(nrm, I_g, I_a)
     assert C.count_bit_mismatches(z.cpu().numpy(), oz) == 0, (cam, "unwarp")
     assert C.count_bit_mismatches(nh.cpu().numpy(), O.normalize(oz)) == 0, (cam, "unwarp+normalize")
-print("TMA_OK")
-''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, VIDC_TMA="1")
-    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0 and "TMA_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+    assert valid.cpu().numpy().min() >= 0 and valid.cpu().numpy().max() <= 1, (cam, "valid flags")
+# signed zeros / denormals / inf / NaN through the same variant
+w, o = Warping2DOFAlignment(*C.CAMERAS["S1"]), O.Oracle(*C.CAMERAS["S1"])
+rgb, depth, nrm = C.special_value_images(4, o.H, o.W, 21)
+I_g, I_a = C.special_value_gravity(4)
+with np.errstate(all="ignore"):
+    _, rgb_w, depth_w, mask = w.warp_rgbd(t(rgb), t(depth), t(I_g), t(I_a))
+    _, nh = w.unwarp_normals(t(nrm), t(I_g), t(I_a))
+    _, oy = o.warp_with_gravity_center_aligned(rgb, I_g, I_a)
+    _, od = o.warp_with_gravity_center_aligned(depth, I_g, I_a)
+    _, oz = o.inverse_warp_normal_image_with_gravity_center_aligned(nrm, I_g, I_a)
+    assert C.count_bit_mismatches(rgb_w.cpu().numpy(), oy) == 0 and C.count_bit_mismatches(depth_w.cpu().numpy().reshape(od.shape), od) == 0
+    assert np.array_equal(mask.cpu().numpy().reshape(-1), O.validity_mask(oy).reshape(-1))
+    assert C.count_bit_mismatches(nh.cpu().numpy(), O.normalize(oz)) == 0
+print("VARIANT_OK")
+'''
+
+
+@pytest.mark.parametrize("env", [{"VIDC_SHEAR": "0"}, {"VIDC_SHEAR": "1"}, {"VIDC_SHEAR": "2"}, {"VIDC_TMA": "1"}],
+                         ids=["straight-rows", "sheared-forward", "sheared-both", "tma-staged"])
+def test_kernel_variants_match_oracle(cuda_device, oracle_mod, env):
+    """Every kernel family behind the fused entry points, each selected by its environment switch in a fresh process:
+    straight row segments (VIDC_SHEAR=0), sheared forward rows (the default), sheared forward + inverse (VIDC_SHEAR=2) and
+    the opt-in TMA-staged kernels (VIDC_TMA=1).  Same bits as the oracle for moderate, extreme (column-major tiles) and
+    edge-case gravity, both depth modes, coverage counts, RGB-only calls, a canvas whose height is not a multiple of
+    the tile (240) and the special-value images."""
+    import os
+    import subprocess
+    import sys
+    code = _VARIANT_CODE % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "VARIANT_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
 
 
 def test_host_buffer_entry_point_pipelined(cuda_device, oracle_mod):
