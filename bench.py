@@ -296,8 +296,8 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_peak()
         px = B * H * W
-        # kernel families behind the fused entry points (vidc_kernels.cu: shear_level(), VIDC_SHEAR, default 1)
-        shear = os.environ.get("VIDC_SHEAR", "1")[:1]
+        # kernel families behind the fused entry points (vidc_kernels.cu: shear_level(), VIDC_SHEAR, default 2)
+        shear = os.environ.get("VIDC_SHEAR", "2")[:1]
         fwd_name = "warp_rgbd_fast_kernel" if shear == "0" else "warp_rgbd_shear_kernel"
         inv_name = "unwarp_normals_shear_kernel" if shear == "2" else "unwarp_normals_fast_kernel"
         dom = (fwd_name, fwd_ms, BYTES_PER_PX_FWD) if fwd_ms >= inv_ms else (inv_name, inv_ms, BYTES_PER_PX_INV)

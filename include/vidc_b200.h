@@ -73,12 +73,13 @@ typedef struct vidc_frame_params {
     float kw, kh;          /* :135-140 */
     float ikw, ikh;        /* "1./kw", "1./kh"  :142-143 */
     float w_max, h_max;    /* :132-133 */
-    float fwd_col_major;   /* 1.0 when output rows of the forward warp run along source columns (|roll| > 45 deg): kernels transpose their thread mapping */
+    float fwd_col_major;   /* 1.0 when canvas rows of the forward warp run along source columns (roll beyond ~76 deg): kernels take column-major tiles */
     float inv_col_major;   /* same for the inverse warp */
     float reserved[11];
 } vidc_frame_params;
 
-/* Logical (N, C, H, W) image batch with element strides. */
+/* Logical (N, C, H, W) image batch with element strides.  N <= 65535 frames per call (they ride on gridDim.z); one
+ * frame must span fewer than 2^31 elements.  Larger batches: call once per slice. */
 typedef struct vidc_image {
     float *data;                 /* device pointer */
     int32_t n, c, h, w;

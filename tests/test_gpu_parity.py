@@ -187,6 +187,11 @@ def test_errors(cuda_device):
         w.warp_rgbd(img, img[:, 0], g, g, depth_mode="linear")
     with pytest.raises(NotImplementedError):                            # valid in torch, never used by the reference
         w.warp_with_gravity_center_aligned(img, g, g, interp_mode="bicubic")
+    wt, _ = _mk("tiny", cuda_device)                                    # frames ride on gridDim.z: explicit limit
+    big = torch.zeros(1, 3, 48, 64, device=cuda_device).expand(65536, 3, 48, 64)
+    gb = g[:1].expand(65536, 3).contiguous()
+    with pytest.raises(RuntimeError, match="65535"):
+        wt.warp_with_gravity_center_aligned(big, gb, gb)
     x = torch.zeros(2, 3, 240, 320, device=cuda_device, requires_grad=True)
     _, y = w.unwarp_normals(x, g, g)                        # fused renormalising entry point: forward-only
     with pytest.raises(NotImplementedError):
@@ -253,7 +258,7 @@ print("VARIANT_OK")
                          ids=["straight-rows", "sheared-forward", "sheared-both", "tma-staged"])
 def test_kernel_variants_match_oracle(cuda_device, oracle_mod, env):
     """Every kernel family behind the fused entry points, each selected by its environment switch in a fresh process:
-    straight row segments (VIDC_SHEAR=0), sheared forward rows (the default), sheared forward + inverse (VIDC_SHEAR=2) and
+    straight row segments (VIDC_SHEAR=0), sheared forward rows only (=1), sheared forward + inverse (=2, the default) and
     the opt-in TMA-staged kernels (VIDC_TMA=1).  Same bits as the oracle for moderate, extreme (column-major tiles) and
     edge-case gravity, both depth modes, coverage counts, RGB-only calls, a canvas whose height is not a multiple of
     the tile (240) and the special-value images."""

@@ -1,10 +1,12 @@
 #!/bin/bash
 # Build-flag sweep on the GPU box: rebuild the library with different tuning macros and time it.
-for cfg in "-DVIDC_SHEAR_MIN_FWD=20 -DVIDC_SHEAR_MIN_INV=40" "-DVIDC_SHEAR_MIN_FWD=10 -DVIDC_SHEAR_MIN_INV=30" "-DVIDC_SHEAR_MIN_FWD=35 -DVIDC_SHEAR_MIN_INV=60" "-DVIDC_SHEAR_MIN_FWD=1000 -DVIDC_SHEAR_MIN_INV=1000"; do
+for cfg in "-DVIDC_SHEAR_BLOCKS_FWD=6 -DVIDC_SHEAR_BLOCKS_INV=7" "-DVIDC_SHEAR_BLOCKS_FWD=6 -DVIDC_SHEAR_BLOCKS_INV=8" "-DVIDC_SHEAR_BLOCKS_FWD=5 -DVIDC_SHEAR_BLOCKS_INV=6"; do
   VIDC_NVCC_EXTRA="$cfg" python -m vi_depth_completion_b200.build --force > /dev/null || { echo build failed; continue; }
-  echo "[$cfg] $(python tools/quick_time.py 2>/dev/null | head -3 | python -c 'import sys,json
-for l in sys.stdin:
-    d=json.loads(l); print("[%s fwd %.3f inv %.3f fps %.0f]"%(d["cam"], d["forward_rgbd_mask"]["ms"], d["inverse_rot_norm"]["ms"], d["frames_per_s"]), end=" ")')"
-  python tools/roll_sweep.py 2>&1 | cut -c1-75
+  echo "[$cfg]"
+  VIDC_SHEAR=2 python bench.py --steps 30 2>/dev/null | tail -1 | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); k=d['roofline']['kernels']
+print('  bench', round(d['value']), {n[:28]: round(v['ms'],4) for n,v in k.items()})"
+  VIDC_SHEAR=2 python tools/roll_sweep.py 2>&1 | cut -c1-75 | sed -n '1p;3p;5p'
 done
 python -m vi_depth_completion_b200.build --force > /dev/null

@@ -24,10 +24,20 @@ namespace vidc_k {
 #ifndef VIDC_SHEAR_MIN_INV
 #define VIDC_SHEAR_MIN_INV 30
 #endif
+// Resident CTAs per SM.  The sheared kernels keep no running output pointers, so they fit 40 / 32 registers and run 6 / 7
+// CTAs per SM where the straight-row kernels run 5 (48 registers): measured on the B200, the extra warps hide more of the
+// gather latency than the smaller L1 (6-7 x 17.5 KB of staging tiles) costs -- inverse 0.538 -> 0.511 ms on the bench
+// workload, 0.547 -> 0.477 ms on level frames (profiles/r1_history.md).
+#ifndef VIDC_SHEAR_BLOCKS_FWD
+#define VIDC_SHEAR_BLOCKS_FWD 6
+#endif
+#ifndef VIDC_SHEAR_BLOCKS_INV
+#define VIDC_SHEAR_BLOCKS_INV 7
+#endif
 constexpr float kShearMinFwd = VIDC_SHEAR_MIN_FWD * 0.01f, kShearMinInv = VIDC_SHEAR_MIN_INV * 0.01f;
 
 template <int GW, int GH, bool HAS_D>
-__global__ void __launch_bounds__(256, VIDC_MIN_BLOCKS)
+__global__ void __launch_bounds__(256, VIDC_SHEAR_BLOCKS_FWD)
 warp_rgbd_shear_kernel(const __grid_constant__ FwdArgs a) {
     static_assert(GW > 0 && GW % 32 == 0, "sheared tiles need a compile-time canvas whose width is a multiple of 32");
     static_assert(ROWS_PER_THREAD == 4 && PATCH_W == 32, "32x32 tile, 8 warps x 4 rows");
@@ -135,7 +145,7 @@ warp_rgbd_shear_kernel(const __grid_constant__ FwdArgs a) {
 // ---- inverse: camera px -> canvas coords, 3 planes, R^T, renormalisation; same sheared rows and staging ----------
 // The fourth component of the staging slot carries the optional validity flag.
 template <int GW, int GH, bool NORMALIZE>
-__global__ void __launch_bounds__(256, VIDC_MIN_BLOCKS)
+__global__ void __launch_bounds__(256, VIDC_SHEAR_BLOCKS_INV)
 unwarp_normals_shear_kernel(const __grid_constant__ InvArgs a) {
     static_assert(GW > 0 && GW % 32 == 0, "sheared tiles need a compile-time canvas whose width is a multiple of 32");
     static_assert(ROWS_PER_THREAD == 4 && PATCH_W == 32, "32x32 tile, 8 warps x 4 rows");
