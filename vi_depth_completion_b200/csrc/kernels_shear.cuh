@@ -16,25 +16,17 @@
 
 namespace vidc_k {
 
-// Tiles whose shear is below these slopes (x 0.01) keep straight rows and store directly, without staging; chosen from
-// the measured cross-over of the two mappings on the B200 (profiles/r1_history.md, threshold sweep).
-#ifndef VIDC_SHEAR_MIN_FWD
-#define VIDC_SHEAR_MIN_FWD 10
-#endif
-#ifndef VIDC_SHEAR_MIN_INV
-#define VIDC_SHEAR_MIN_INV 30
-#endif
-// Resident CTAs per SM.  The sheared kernels keep no running output pointers, so they fit 40 / 32 registers and run 6 / 7
-// CTAs per SM where the straight-row kernels run 5 (48 registers): measured on the B200, the extra warps hide more of the
-// gather latency than the smaller L1 (6-7 x 17.5 KB of staging tiles) costs -- inverse 0.538 -> 0.511 ms on the bench
-// workload, 0.547 -> 0.477 ms on level frames (profiles/r1_history.md).
+// Resident CTAs per SM.  The sheared kernels keep no running output pointers, so their hot paths fit 32 registers (the
+// few spills sit in the cold column-major path) and 8 CTAs = 64 warps are resident per SM, where the straight-row kernels
+// run 5 CTAs at 48 registers.  Measured on the B200 the extra warps hide more of the gather latency than the smaller L1
+// (8 x 17.5 KB of staging tiles) costs: forward 0.641 -> 0.621 ms, inverse 0.538 -> 0.510 ms on the bench workload,
+// 0.695 -> 0.642 / 0.547 -> 0.477 ms on level frames (profiles/r1_history.md, occupancy sweep).
 #ifndef VIDC_SHEAR_BLOCKS_FWD
-#define VIDC_SHEAR_BLOCKS_FWD 6
+#define VIDC_SHEAR_BLOCKS_FWD 8
 #endif
 #ifndef VIDC_SHEAR_BLOCKS_INV
-#define VIDC_SHEAR_BLOCKS_INV 7
+#define VIDC_SHEAR_BLOCKS_INV 8
 #endif
-constexpr float kShearMinFwd = VIDC_SHEAR_MIN_FWD * 0.01f, kShearMinInv = VIDC_SHEAR_MIN_INV * 0.01f;
 
 template <int GW, int GH, bool HAS_D>
 __global__ void __launch_bounds__(256, VIDC_SHEAR_BLOCKS_FWD)
@@ -64,17 +56,14 @@ warp_rgbd_shear_kernel(const __grid_constant__ FwdArgs a) {
     const float* __restrict__ in_dep = HAS_D ? a.dep + (long long)b * a.dep_sn : nullptr;
     // shear of this tile: d(source y)/dX and /dY of the canvas -> source map at the tile centre (not part of any result)
     int sh_l;
-    bool direct;
     {
         const float pxc = ikw * (float)(blockIdx.x * TILE_W + TILE_W / 2) + px_min;
         const float pyc = ikh * (float)(tileY0 + TILE_H / 2) + py_min;
         const float vc = fmaf(Hi[4], pyc, Hi[3] * pxc) + Hi[5], sc = fmaf(Hi[7], pyc, Hi[6] * pxc) + Hi[8];
         float slope = -__fdividef(ikw * (Hi[3] * sc - vc * Hi[6]), ikh * (Hi[4] * sc - vc * Hi[7]));
         slope = fminf(fmaxf(slope, -4.0f), 4.0f);                  // NaN -> -4: any integer shear is a valid permutation
-        direct = fabsf(slope) < kShearMinFwd;                      // nearly level tile: straight rows, direct stores
-        sh_l = direct ? 0 : __float2int_rn(slope * (float)lane);
+        sh_l = __float2int_rn(slope * (float)lane);
     }
-    unsigned int cnt = 0;
 #pragma unroll
     for (int j = 0; j < ROWS_PER_THREAD; ++j) {
         const int Ys = (warp * ROWS_PER_THREAD + j + sh_l) & 31;
@@ -89,26 +78,13 @@ warp_rgbd_shear_kernel(const __grid_constant__ FwdArgs a) {
         const float ix = unnormalize(gx, Wf), iy = unnormalize(gy, Hf);
         const Pos t = make_pos(ix, iy, H, W);
         const Px4 o = fwd_sample_row<HAS_D>(in_rgb, in_dep, W, W * H, H, W, a.mode_d, ix, iy, t);
-        if (direct) {                                              // CTA-uniform
-            const bool live = H % 32 == 0 || tileY0 + Ys < H;
-            const bool m = (o.r + o.g) + o.b > 0.01f;              // surface_normal.py:151
-            if (live) {
-                float* __restrict__ o_rgb = a.rgb_o + ((long long)b * a.rgbo_sn + (tileY0 + Ys) * W + X);
-                o_rgb[0] = o.r; o_rgb[W * H] = o.g; o_rgb[2 * W * H] = o.b;
-                if (HAS_D) a.dep_o[(long long)b * a.depo_sn + (tileY0 + Ys) * W + X] = o.d;
-                if (a.mask) a.mask[((long long)b * H + tileY0 + Ys) * W + X] = m ? 1 : 0;
-            }
-            if (a.coverage) cnt += (m && live) ? 1u : 0u;
-        } else {
-            tile[Ys][lane ^ (lane >> 3)] = make_float4(o.r, o.g, o.b, o.d);
-        }
+        tile[Ys][lane ^ (lane >> 3)] = make_float4(o.r, o.g, o.b, o.d);
     }
-    const int tid = warp * 32 + lane;
-    if (!direct) {
     __syncthreads();
     // write-out: thread -> (row, 4 consecutive columns), 128-bit loads from the tile, 128-bit row stores
-    const int row = tid >> 3, c4 = (tid & 7) * 4;
+    const int tid = warp * 32 + lane, row = tid >> 3, c4 = (tid & 7) * 4;
     const int Yo = tileY0 + row, Xo = blockIdx.x * TILE_W + c4;
+    unsigned int cnt = 0;
     if (H % 32 == 0 || Yo < H) {
         float4 px4[4];
 #pragma unroll
@@ -129,7 +105,6 @@ warp_rgbd_shear_kernel(const __grid_constant__ FwdArgs a) {
             if (a.mask) *reinterpret_cast<unsigned int*>(a.mask + (((long long)b * H + Yo) * W + Xo)) = m0 | (m1 << 8) | (m2 << 16) | (m3 << 24);
             cnt = m0 + m1 + m2 + m3;
         }
-    }
     }
     if (a.coverage) {
         __shared__ unsigned int cta_cov;
@@ -168,14 +143,12 @@ unwarp_normals_shear_kernel(const __grid_constant__ InvArgs a) {
     const float Wf = (float)W, Hf = (float)H;
     const float* __restrict__ in = a.x + (long long)b * a.x_sn;
     int sh_l;
-    bool direct;
     {
         const float xc = (float)(blockIdx.x * TILE_W + TILE_W / 2), yc = (float)(tileY0 + TILE_H / 2);
         const float vc = fmaf(Hm[4], yc, Hm[3] * xc) + Hm[5], sc = fmaf(Hm[7], yc, Hm[6] * xc) + Hm[8];
         float slope = -__fdividef(Hm[3] * sc - vc * Hm[6], Hm[4] * sc - vc * Hm[7]);
         slope = fminf(fmaxf(slope, -4.0f), 4.0f);
-        direct = fabsf(slope) < kShearMinInv;
-        sh_l = direct ? 0 : __float2int_rn(slope * (float)lane);
+        sh_l = __float2int_rn(slope * (float)lane);
     }
 #pragma unroll
     for (int j = 0; j < ROWS_PER_THREAD; ++j) {
@@ -197,17 +170,8 @@ unwarp_normals_shear_kernel(const __grid_constant__ InvArgs a) {
         float z1 = fmaf(R[7], y.c, fmaf(R[4], y.b, fmaf(R[1], y.a, 0.0f)));
         float z2 = fmaf(R[8], y.c, fmaf(R[5], y.b, fmaf(R[2], y.a, 0.0f)));
         if (NORMALIZE) normalize3_rn(z0, z1, z2);                  // surface_normal.py:170
-        if (direct) {                                              // CTA-uniform
-            if (H % 32 == 0 || tileY0 + Ys < H) {
-                float* __restrict__ o = a.z + ((long long)b * a.z_sn + (tileY0 + Ys) * W + X);
-                o[0] = z0; o[W * H] = z1; o[2 * W * H] = z2;
-                if (a.valid) a.valid[((long long)b * H + tileY0 + Ys) * W + X] = t.touch ? 1 : 0;
-            }
-        } else {
-            tile[Ys][lane ^ (lane >> 3)] = make_float4(z0, z1, z2, (a.valid && t.touch) ? 1.0f : 0.0f);
-        }
+        tile[Ys][lane ^ (lane >> 3)] = make_float4(z0, z1, z2, (a.valid && t.touch) ? 1.0f : 0.0f);
     }
-    if (direct) return;
     __syncthreads();
     const int tid = warp * 32 + lane, row = tid >> 3, c4 = (tid & 7) * 4;
     const int Yo = tileY0 + row, Xo = blockIdx.x * TILE_W + c4;
