@@ -1,12 +1,12 @@
 #!/bin/bash
 # Build-flag sweep on the GPU box: rebuild the library with different tuning macros and time it.
-for cfg in "-DVIDC_SHEAR_MIN_FWD=0 -DVIDC_SHEAR_MIN_INV=0" "-DVIDC_SHEAR_MIN_FWD=10 -DVIDC_SHEAR_MIN_INV=30" "-DVIDC_SHEAR_MIN_FWD=25 -DVIDC_SHEAR_MIN_INV=15"; do
+for cfg in "-DVIDC_SHEAR_EPILOGUE_IN_LOOP=1 -DVIDC_SHEAR_BLOCKS_INV=8" "-DVIDC_SHEAR_EPILOGUE_IN_LOOP=1 -DVIDC_SHEAR_BLOCKS_INV=6"; do
   VIDC_NVCC_EXTRA="$cfg" python -m vi_depth_completion_b200.build --force > /dev/null || { echo build failed; continue; }
   echo "[$cfg]"
   python bench.py --steps 30 2>/dev/null | tail -1 | python -c "
 import sys,json
 d=json.loads(sys.stdin.read()); k=d['roofline']['kernels']
 print('  bench', round(d['value']), {n[:28]: round(v['ms'],4) for n,v in k.items()})"
-  python tools/roll_sweep.py 2>&1 | cut -c1-75 | sed -n '1,5p'
+  python tools/roll_sweep.py 2>&1 | cut -c1-75
 done
 python -m vi_depth_completion_b200.build --force > /dev/null
