@@ -228,6 +228,11 @@ for cam, (I_g, I_a) in (("S1", C.random_gravity(6, 1234)), ("S2", C.random_gravi
         assert C.count_bit_mismatches(depth_w.cpu().numpy(), od) == 0, (cam, mode, "depth")
         assert np.array_equal(mask.cpu().numpy(), om), (cam, mode, "mask")
         assert np.array_equal(cov.cpu().numpy().astype(np.int64), om.reshape(B, -1).sum(1).astype(np.int64)), (cam, mode, "coverage")
+        _, y3 = w.warp_with_gravity_center_aligned(t(rgb), t(I_g), t(I_a), interp_mode=mode)       # reference-shaped calls
+        _, y1 = w.warp_with_gravity_center_aligned(t(depth), t(I_g), t(I_a), interp_mode=mode)     # 3-D depth path (:110-112)
+        _, o3 = o.warp_with_gravity_center_aligned(rgb, I_g, I_a, interp_mode=mode)
+        assert C.count_bit_mismatches(y3.cpu().numpy(), o3) == 0, (cam, mode, "warp_with_gravity_center_aligned rgb")
+        assert y1.dim() == 3 and C.count_bit_mismatches(y1.cpu().numpy(), od) == 0, (cam, mode, "warp_with_gravity_center_aligned depth")
     _, rgb_only, _, mask_only = w.warp_rgbd(t(rgb), None, t(I_g), t(I_a))
     assert C.count_bit_mismatches(rgb_only.cpu().numpy(), oy) == 0 and np.array_equal(mask_only.cpu().numpy(), om), (cam, "rgb only")
     nrm = C.random_images(B, o.H, o.W, 6)[2]

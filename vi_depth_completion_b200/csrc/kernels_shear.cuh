@@ -164,6 +164,113 @@ warp_rgbd_shear_kernel(const __grid_constant__ FwdArgs a) {
     warp_rgbd_shear_write_out<GW, GH, HAS_D, false>(a, tile);
 }
 
+// ---- forward, C planes in one interpolation mode: the reference-shaped call warp_with_gravity_center_aligned ------------
+// (RGB: C = 3; depth through the 3-D path of :110-112: C = 1).  Same segments, staging and write-out; no mask.
+struct PlanesArgs {
+    const vidc_frame_params* prm; CamConst cam;
+    const float* x; long long x_sn;         // input planes, contiguous W x H each
+    float* y; long long y_sn;               // canvas planes, contiguous W x H each
+    int mode;
+};
+
+template <int GW, int GH, int C, bool ALONG_Y>
+__device__ __forceinline__ void warp_planes_shear_segments(const PlanesArgs& a, const float* pr, float4 (*tile)[32], int sh_l) {
+    constexpr int W = GW, H = GH;
+    const int b = blockIdx.z, lane = threadIdx.x, warp = threadIdx.y;
+    const int tileX0 = blockIdx.x * TILE_W, tileY0 = blockIdx.y * TILE_H;
+    const float* Hi = pr + 2;
+    const float px_min = pr[11], py_min = pr[12], ikw = pr[15], ikh = pr[16];
+    const float Wf = (float)W, Hf = (float)H;
+    const float* __restrict__ in = a.x + (long long)b * a.x_sn;
+    const float p_fix = ALONG_Y ? ikh * (float)(tileY0 + lane) + py_min : ikw * (float)(tileX0 + lane) + px_min;
+    const float u0 = Hi[0] * p_fix, v0 = Hi[3] * p_fix, s0 = Hi[6] * p_fix;
+#pragma unroll
+    for (int j = 0; j < ROWS_PER_THREAD; ++j) {
+        const int S = (warp * ROWS_PER_THREAD + j + sh_l) & 31;
+        float u, v, s;
+        if (ALONG_Y) {
+            const float px = ikw * (float)(tileX0 + S) + px_min;
+            u = fmaf(Hi[1], p_fix, Hi[0] * px) + Hi[2];
+            v = fmaf(Hi[4], p_fix, Hi[3] * px) + Hi[5];
+            s = fmaf(Hi[7], p_fix, Hi[6] * px) + Hi[8];
+        } else {
+            const float py = ikh * (float)(tileY0 + S) + py_min;
+            u = fmaf(Hi[1], py, u0) + Hi[2];
+            v = fmaf(Hi[4], py, v0) + Hi[5];
+            s = fmaf(Hi[7], py, s0) + Hi[8];
+        }
+        float sx, sy;
+        div2_rn(u, v, s, sx, sy);                                  // :146-147
+        const float gx = a.cam.inv_half_w * (sx - a.cam.cx);
+        const float gy = a.cam.inv_half_h * (sy - a.cam.cy);
+        const float ix = unnormalize(gx, Wf), iy = unnormalize(gy, Hf);
+        const Pos t = make_pos(ix, iy, H, W);
+        float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (__any_sync(0xffffffffu, t.touch)) {                    // exterior segments: zeros
+            if (a.mode != VIDC_BILINEAR) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) o[c] = sample_nearest_pos(in + c * (W * H), ix, iy, H, W, W, t.touch);
+            } else if (__all_sync(0xffffffffu, t.interior)) {
+                const int off = t.y0 * W + t.x0;
+#pragma unroll
+                for (int c = 0; c < C; ++c) o[c] = sample_interior(in + c * (W * H), off, W, t);
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; ++c) o[c] = sample_border(in + c * (W * H), W, H, W, t);
+            }
+        }
+        const int row = ALONG_Y ? lane : S, col = ALONG_Y ? S : lane;
+        tile[row][shear_slot<ALONG_Y>(row, col)] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+template <int GW, int GH, int C, bool ALONG_Y>
+__device__ __forceinline__ void warp_planes_shear_write_out(const PlanesArgs& a, const float4 (*tile)[32]) {
+    constexpr int W = GW, H = GH;
+    const int b = blockIdx.z, tid = threadIdx.y * 32 + threadIdx.x, row = tid >> 3, c4 = (tid & 7) * 4;
+    const int Yo = blockIdx.y * TILE_H + row, Xo = blockIdx.x * TILE_W + c4;
+    if (H % 32 == 0 || Yo < H) {
+        float4 px4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) px4[k] = tile[row][shear_slot<ALONG_Y>(row, c4 + k)];
+        float* __restrict__ o = a.y + ((long long)b * a.y_sn + Yo * W + Xo);
+        *reinterpret_cast<float4*>(o) = make_float4(px4[0].x, px4[1].x, px4[2].x, px4[3].x);
+        if (C > 1) *reinterpret_cast<float4*>(o + W * H) = make_float4(px4[0].y, px4[1].y, px4[2].y, px4[3].y);
+        if (C > 2) *reinterpret_cast<float4*>(o + 2 * W * H) = make_float4(px4[0].z, px4[1].z, px4[2].z, px4[3].z);
+        if (C > 3) *reinterpret_cast<float4*>(o + 3 * W * H) = make_float4(px4[0].w, px4[1].w, px4[2].w, px4[3].w);
+    }
+}
+
+template <int GW, int GH, int C>
+__global__ void __launch_bounds__(256, VIDC_SHEAR_BLOCKS_FWD)
+warp_planes_shear_kernel(const __grid_constant__ PlanesArgs a) {
+    static_assert(GW > 0 && GW % 32 == 0 && C >= 1 && C <= 4, "compile-time canvas, 1-4 planes");
+    static_assert(ROWS_PER_THREAD == 4 && PATCH_W == 32 && TILE_W == 32 && TILE_H == 32, "32x32 tile, 8 warps x 4 segments");
+    __shared__ __align__(16) float4 tile[32][32];
+    const int b = blockIdx.z, lane = threadIdx.x;
+    const int tileX0 = blockIdx.x * TILE_W, tileY0 = blockIdx.y * TILE_H;
+    float pr[20];
+    load_params(a.prm + b, pr, 4, 5);
+    int sh_l;
+    bool along_y;
+    {
+        const float* Hi = pr + 2;
+        const float ikw = pr[15], ikh = pr[16];
+        const float pxc = ikw * (float)(tileX0 + TILE_W / 2) + pr[11], pyc = ikh * (float)(tileY0 + TILE_H / 2) + pr[12];
+        const float vc = fmaf(Hi[4], pyc, Hi[3] * pxc) + Hi[5], sc = fmaf(Hi[7], pyc, Hi[6] * pxc) + Hi[8];
+        along_y = shear_of_tile(ikw * (Hi[3] * sc - vc * Hi[6]), ikh * (Hi[4] * sc - vc * Hi[7]), lane, sh_l);
+    }
+    if (along_y) {                                                 // CTA-uniform
+        warp_planes_shear_segments<GW, GH, C, true>(a, pr, tile, sh_l);
+        __syncthreads();
+        warp_planes_shear_write_out<GW, GH, C, true>(a, tile);
+        return;
+    }
+    warp_planes_shear_segments<GW, GH, C, false>(a, pr, tile, sh_l);
+    __syncthreads();
+    warp_planes_shear_write_out<GW, GH, C, false>(a, tile);
+}
+
 // ---- inverse: camera px -> canvas coords, 3 planes, R^T, renormalisation ------------------------------------------------
 // The fourth component of the staging slot carries the optional validity flag.
 template <int GW, int GH, bool NORMALIZE, bool ALONG_Y>
