@@ -245,6 +245,51 @@ __global__ void __launch_bounds__(256) normalize3_kernel(ImgView z, ImgViewOut o
     q[0] = z0 / n; q[o.sc] = z1 / n; q[2 * o.sc] = z2 / n;
 }
 
+// Contiguous planes (the common case): four pixels per thread, 128-bit loads and stores, grid-stride over the frame.
+// hw4 = H * W / 4; planes are hw4 float4s apart; frames are z_sn / o_sn floats apart.
+__global__ void __launch_bounds__(256) normalize3_vec4_kernel(const float* __restrict__ z, long long z_sn, float* __restrict__ o,
+                                                              long long o_sn, int hw4) {
+    const int b = blockIdx.y;
+    const float4* __restrict__ p = reinterpret_cast<const float4*>(z + (long long)b * z_sn);
+    float4* __restrict__ q = reinterpret_cast<float4*>(o + (long long)b * o_sn);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw4; i += gridDim.x * blockDim.x) {
+        const float4 a0 = __ldg(p + i), a1 = __ldg(p + hw4 + i), a2 = __ldg(p + 2 * hw4 + i);
+        float4 r0, r1, r2;
+        float n;
+        n = clamp_min_eps(sqrtf((a0.x * a0.x + a1.x * a1.x) + a2.x * a2.x)); r0.x = a0.x / n; r1.x = a1.x / n; r2.x = a2.x / n;
+        n = clamp_min_eps(sqrtf((a0.y * a0.y + a1.y * a1.y) + a2.y * a2.y)); r0.y = a0.y / n; r1.y = a1.y / n; r2.y = a2.y / n;
+        n = clamp_min_eps(sqrtf((a0.z * a0.z + a1.z * a1.z) + a2.z * a2.z)); r0.z = a0.z / n; r1.z = a1.z / n; r2.z = a2.z / n;
+        n = clamp_min_eps(sqrtf((a0.w * a0.w + a1.w * a1.w) + a2.w * a2.w)); r0.w = a0.w / n; r1.w = a1.w / n; r2.w = a2.w / n;
+        q[i] = r0; q[hw4 + i] = r1; q[2 * hw4 + i] = r2;
+    }
+}
+// surface_normal.py:151 on contiguous planes: four pixels per thread, u8 and / or float mask, coverage by popc
+__global__ void __launch_bounds__(256) validity_mask_vec4_kernel(const float* __restrict__ x, long long x_sn, int hw4,
+                                                                 unsigned char* __restrict__ mu8, float* __restrict__ mf32,
+                                                                 unsigned int* __restrict__ coverage) {
+    const int b = blockIdx.y;
+    const float4* __restrict__ p = reinterpret_cast<const float4*>(x + (long long)b * x_sn);
+    unsigned int cnt = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw4; i += gridDim.x * blockDim.x) {
+        const float4 r = __ldg(p + i), g = __ldg(p + hw4 + i), bl = __ldg(p + 2 * hw4 + i);
+        const unsigned int m0 = (r.x + g.x) + bl.x > 0.01f, m1 = (r.y + g.y) + bl.y > 0.01f;
+        const unsigned int m2 = (r.z + g.z) + bl.z > 0.01f, m3 = (r.w + g.w) + bl.w > 0.01f;
+        const long long o4 = (long long)b * hw4 + i;
+        if (mu8) reinterpret_cast<unsigned int*>(mu8)[o4] = m0 | (m1 << 8) | (m2 << 16) | (m3 << 24);
+        if (mf32) reinterpret_cast<float4*>(mf32)[o4] = make_float4((float)m0, (float)m1, (float)m2, (float)m3);
+        cnt += m0 + m1 + m2 + m3;
+    }
+    if (coverage) {
+        __shared__ unsigned int cta_count;
+        if (threadIdx.x == 0) cta_count = 0;
+        __syncthreads();
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&cta_count, cnt);
+        __syncthreads();
+        if (threadIdx.x == 0 && cta_count) atomicAdd(coverage + b, cta_count);
+    }
+}
+
 // normal_utils.py:7-34 in one pass; fp64 block reduction (warp shuffles), one atomic per CTA per stat
 __global__ void __launch_bounds__(256)
 normal_stats_kernel(ImgView gt, ImgView pred, ImgView mask, int normalize_prediction, double* __restrict__ out) {
