@@ -1,6 +1,6 @@
 #!/bin/bash
 # Build-flag sweep on the GPU box: rebuild the library with different tuning macros and time it.
-for cfg in "-DVIDC_SHEAR_EPILOGUE_IN_LOOP=1 -DVIDC_SHEAR_BLOCKS_INV=8" "-DVIDC_SHEAR_EPILOGUE_IN_LOOP=1 -DVIDC_SHEAR_BLOCKS_INV=6"; do
+for cfg in "-DVIDC_SHEAR_BLOCKS_FWD=6" "-DVIDC_SHEAR_BLOCKS_FWD=5"; do
   VIDC_NVCC_EXTRA="$cfg" python -m vi_depth_completion_b200.build --force > /dev/null || { echo build failed; continue; }
   echo "[$cfg]"
   python bench.py --steps 30 2>/dev/null | tail -1 | python -c "

@@ -27,6 +27,17 @@
 
 namespace vidc_k {
 
+// Segment (before the shear) that warp w processes in its j-th iteration.  Interleaved (w + 8 j): the eight warps of a
+// CTA work on eight ADJACENT segments at any time, so the source lines two neighbouring segments share are reused while
+// they are still in L1; blocked (4 w + j) leaves that reuse to the next iteration, after 63 other warps have gone through L1.
+#ifndef VIDC_SEG_INTERLEAVED
+#define VIDC_SEG_INTERLEAVED 1
+#endif
+#if VIDC_SEG_INTERLEAVED
+#define VIDC_SEG(w, j) ((w) + 8 * (j))
+#else
+#define VIDC_SEG(w, j) ((w) * ROWS_PER_THREAD + (j))
+#endif
 #ifndef VIDC_SHEAR_BLOCKS_FWD
 #define VIDC_SHEAR_BLOCKS_FWD 8
 #endif
@@ -67,7 +78,7 @@ __device__ __forceinline__ void warp_rgbd_shear_segments(const FwdArgs& a, const
     const float u0 = Hi[0] * p_fix, v0 = Hi[3] * p_fix, s0 = Hi[6] * p_fix;        // used when the fixed one is X
 #pragma unroll
     for (int j = 0; j < ROWS_PER_THREAD; ++j) {
-        const int S = (warp * ROWS_PER_THREAD + j + sh_l) & 31;
+        const int S = (VIDC_SEG(warp, j) + sh_l) & 31;
         float u, v, s;
         if (ALONG_Y) {
             const float px = ikw * (float)(tileX0 + S) + px_min;
@@ -186,7 +197,7 @@ __device__ __forceinline__ void warp_planes_shear_segments(const PlanesArgs& a, 
     const float u0 = Hi[0] * p_fix, v0 = Hi[3] * p_fix, s0 = Hi[6] * p_fix;
 #pragma unroll
     for (int j = 0; j < ROWS_PER_THREAD; ++j) {
-        const int S = (warp * ROWS_PER_THREAD + j + sh_l) & 31;
+        const int S = (VIDC_SEG(warp, j) + sh_l) & 31;
         float u, v, s;
         if (ALONG_Y) {
             const float px = ikw * (float)(tileX0 + S) + px_min;
@@ -287,7 +298,7 @@ __device__ __forceinline__ void unwarp_normals_shear_segments(const InvArgs& a, 
     const float u0 = Hm[0] * c_fix, v0 = Hm[3] * c_fix, s0 = Hm[6] * c_fix;        // used when the fixed one is X
 #pragma unroll
     for (int j = 0; j < ROWS_PER_THREAD; ++j) {
-        const int S = (warp * ROWS_PER_THREAD + j + sh_l) & 31;
+        const int S = (VIDC_SEG(warp, j) + sh_l) & 31;
         float u, v, s;
         if (ALONG_Y) {
             const float Xf = (float)(tileX0 + S);
