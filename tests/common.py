@@ -131,6 +131,16 @@ def degenerate_gravity():
     return g, a
 
 
+def isolated_nonfinite_gravity():
+    """Steep-pitch gravity vectors (found by search at 320x240, S1 intrinsics) for which the projective denominator is
+    EXACTLY zero at a single pixel of the forward and / or inverse grid: one lane of a warp has a non-finite sampling
+    coordinate while its neighbours are finite.  That lane must read as out of bounds (0), like ATen's CUDA kernel."""
+    g = np.array([[0.06171473, 0.30808246, -0.94935584], [-0.13590553, 0.21624178, -0.9668346],
+                  [-0.04061935, 0.31595406, 0.9479046], [-0.09833453, 0.21313821, 0.9720609]], np.float32)
+    a = np.tile(np.array([[0.0, 1.0, 0.0]], np.float32), (g.shape[0], 1))
+    return g, a
+
+
 def smooth_images(B, H, W, seed):
     """Low-frequency images (real photographs are smooth): sums of a few sinusoids."""
     rs = np.random.RandomState(seed)

@@ -476,3 +476,34 @@ def test_degenerate_gravity_matches_oracle(cuda_device, oracle_mod):
         assert np.array_equal(mask.cpu().numpy().reshape(-1), O.validity_mask(oy).reshape(-1))
         assert C.count_bit_mismatches(z.cpu().numpy(), oz) == 0
         assert C.count_bit_mismatches(nhat.cpu().numpy(), ozn) == 0
+
+
+def test_isolated_nonfinite_coordinate_inside_a_warp(cuda_device, oracle_mod):
+    """A projective denominator that is exactly 0 at one pixel: that lane's coordinate is inf / NaN while the rest of its
+    warp samples normally.  The pixel must come out 0 (out of bounds), not NaN from 0 * NaN weights."""
+    from oracle import oracle as O
+    w, o = _mk("S1", cuda_device)
+    I_g, I_a = C.isolated_nonfinite_gravity()
+    B, Hh, Ww = I_g.shape[0], int(w.H), int(w.W)
+    with np.errstate(all="ignore"):
+        _, ogrid, oinv = o.image_sampler_forward_inverse(I_g, I_a)
+    assert 0 < (~np.isfinite(ogrid)).sum() + (~np.isfinite(oinv)).sum() < 64         # the cases are really in there
+    rgb, depth, normals = C.random_images(B, Hh, Ww, seed=9)
+    g, a = _t(I_g, cuda_device), _t(I_a, cuda_device)
+    for env_ok in (True,):
+        _, rgb_w, depth_w, mask = w.warp_rgbd(_t(rgb, cuda_device), _t(depth, cuda_device), g, a)
+        _, y = w.warp_with_gravity_center_aligned(_t(rgb, cuda_device), g, a)
+        _, z = w.inverse_warp_normal_image_with_gravity_center_aligned(_t(normals, cuda_device), g, a)
+        _, nhat = w.unwarp_normals(_t(normals, cuda_device), g, a)
+    with np.errstate(all="ignore"):
+        _, oy = o.warp_with_gravity_center_aligned(rgb, I_g, I_a)
+        _, oyd = o.warp_with_gravity_center_aligned(depth, I_g, I_a)
+        _, oz = o.inverse_warp_normal_image_with_gravity_center_aligned(normals, I_g, I_a)
+        ozn = O.normalize(oz)
+    assert not np.isnan(rgb_w.cpu().numpy()).any() and not np.isnan(z.cpu().numpy()).any()
+    assert C.count_bit_mismatches(rgb_w.cpu().numpy(), oy) == 0
+    assert C.count_bit_mismatches(y.cpu().numpy(), oy) == 0
+    assert C.count_bit_mismatches(depth_w.cpu().numpy().reshape(oyd.shape), oyd) == 0
+    assert np.array_equal(mask.cpu().numpy().reshape(-1), O.validity_mask(oy).reshape(-1))
+    assert C.count_bit_mismatches(z.cpu().numpy(), oz) == 0
+    assert C.count_bit_mismatches(nhat.cpu().numpy(), ozn) == 0

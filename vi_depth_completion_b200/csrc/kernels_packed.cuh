@@ -75,7 +75,7 @@ warp_rgbd_nhwc4_kernel(const __grid_constant__ PackedArgs a) {
                 const float4 ne = (t.touch && in_x1 && in_y0) ? __ldg(p + 1) : zero4;
                 const float4 sw = (t.touch && in_x0 && in_y1) ? __ldg(p + Win) : zero4;
                 const float4 se = (t.touch && in_x1 && in_y1) ? __ldg(p + Win + 1) : zero4;
-                r = bilerp_px(nw, ne, sw, se, t);
+                r = t.touch ? bilerp_px(nw, ne, sw, se, t) : zero4;      // non-finite coordinate: NaN weights, reads as 0
             }
             if (a.mode_d != VIDC_BILINEAR) {   // depth channel by nearest neighbour
                 const int xn = (int)rintf(ix), yn = (int)rintf(iy);
