@@ -320,16 +320,18 @@ def test_packed_rgbd_nhwc4_matches_oracle(cuda_device, oracle_mod):
             assert np.array_equal(cov.cpu().numpy(), mask.cpu().numpy().reshape(B, -1).sum(1))
 
 
-@pytest.mark.parametrize("intr", [(120.0, 118.0, 100.3, 70.2), (90.0, 95.0, 33.4, 47.9), (300.0, 300.0, 256.0, 128.0)])
+@pytest.mark.parametrize("intr", [(120.0, 118.0, 100.3, 70.2), (90.0, 95.0, 33.4, 47.9), (300.0, 300.0, 256.0, 128.0),
+                                  (90.0, 95.0, 47.9, 24.7), (500.0, 500.0, 319.9, 244.3)])
 def test_odd_canvas_sizes(cuda_device, oracle_mod, intr):
-    """Canvas sizes that are not multiples of the 32x32 tile (201x141, 67x96) and a wide 512x256 one: the fast kernels'
-    runtime-geometry instantiation and the generic-stride kernels, inputs of a different size than the canvas, strided views."""
+    """Canvas sizes that are not multiples of the 32x32 tile (201x141, 67x96: straight-row runtime-geometry kernels), widths
+    that are (512x256, 96x50, 640x489 -- the real Azure Kinect canvas: sheared runtime-geometry kernels, the last two with
+    a bottom tile row that overhangs), the generic-stride kernels, inputs of a different size than the canvas, strided views."""
     from vi_depth_completion_b200.warping_2dof_alignment import Warping2DOFAlignment
     fx, fy, cx, cy = intr
     w, o = Warping2DOFAlignment(fx=fx, fy=fy, cx=cx, cy=cy), oracle_mod.Oracle(fx, fy, cx, cy)
     assert (int(w.W), int(w.H)) == (o.W, o.H)
     B = 5
-    I_g, I_a = C.random_gravity(B, seed=8, roll_deg=40, pitch_deg=30)
+    I_g, I_a = C.random_gravity(B, seed=8, roll_deg=80, pitch_deg=30)       # both shear orientations
     rgb, depth, normals = C.random_images(B, o.H, o.W, seed=3)
     g, a = _t(I_g, cuda_device), _t(I_a, cuda_device)
     _, rgb_w, depth_w, mask = w.warp_rgbd(_t(rgb, cuda_device), _t(depth, cuda_device), g, a)

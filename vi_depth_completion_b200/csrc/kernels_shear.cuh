@@ -21,8 +21,8 @@
 // straight-row kernels run 5 CTAs at 48 registers, which hides more of the gather latency than the smaller L1
 // (8 x 16 KB of staging tiles) costs (profiles/r1_history.md, occupancy sweep).
 //
-// Compile-time geometry only (W a multiple of 32, contiguous planes, 16-byte aligned outputs); everything else takes
-// the straight-row kernels of kernels_fast.cuh.
+// Contiguous planes whose width is a multiple of 32 (compile-time 640x480 and 320x240, or runtime geometry with input and
+// canvas of the same size), 16-byte aligned outputs; everything else takes the straight-row kernels of kernels_fast.cuh.
 #pragma once
 
 namespace vidc_k {
@@ -37,6 +37,10 @@ namespace vidc_k {
 #define VIDC_SEG(w, j) ((w) + 8 * (j))
 #else
 #define VIDC_SEG(w, j) ((w) * ROWS_PER_THREAD + (j))
+#endif
+// runtime-geometry instantiations (GW = GH = 0) carry W, H and W * H in registers
+#ifndef VIDC_SHEAR_BLOCKS_RT
+#define VIDC_SHEAR_BLOCKS_RT 6
 #endif
 #ifndef VIDC_SHEAR_BLOCKS_FWD
 #define VIDC_SHEAR_BLOCKS_FWD 8
@@ -65,7 +69,7 @@ __device__ __forceinline__ bool shear_of_tile(float ax, float ay, int lane, int&
 // ---- forward: RGB (3 planes) + optional depth, mask, coverage -------------------------------------------------------
 template <int GW, int GH, bool HAS_D, bool ALONG_Y>
 __device__ __forceinline__ void warp_rgbd_shear_segments(const FwdArgs& a, const float* pr, float4 (*tile)[32], int sh_l) {
-    constexpr int W = GW, H = GH;
+    const int W = GW ? GW : a.cam.W, H = GW ? GH : a.cam.H;
     const int b = blockIdx.z, lane = threadIdx.x, warp = threadIdx.y;
     const int tileX0 = blockIdx.x * TILE_W, tileY0 = blockIdx.y * TILE_H;
     const float* Hi = pr + 2;
@@ -106,12 +110,12 @@ __device__ __forceinline__ void warp_rgbd_shear_segments(const FwdArgs& a, const
 // write-out: thread -> (row, 4 consecutive columns), 128-bit loads from the tile, 128-bit row stores per plane
 template <int GW, int GH, bool HAS_D, bool ALONG_Y>
 __device__ __forceinline__ void warp_rgbd_shear_write_out(const FwdArgs& a, const float4 (*tile)[32]) {
-    constexpr int W = GW, H = GH;
+    const int W = GW ? GW : a.cam.W, H = GW ? GH : a.cam.H;
     const int b = blockIdx.z, lane = threadIdx.x, warp = threadIdx.y;
     const int tid = warp * 32 + lane, row = tid >> 3, c4 = (tid & 7) * 4;
     const int Yo = blockIdx.y * TILE_H + row, Xo = blockIdx.x * TILE_W + c4;
     unsigned int cnt = 0;
-    if (H % 32 == 0 || Yo < H) {
+    if ((GW && GH % 32 == 0) || Yo < H) {
         float4 px4[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) px4[k] = tile[row][shear_slot<ALONG_Y>(row, c4 + k)];
@@ -144,11 +148,11 @@ __device__ __forceinline__ void warp_rgbd_shear_write_out(const FwdArgs& a, cons
 }
 
 template <int GW, int GH, bool HAS_D>
-__global__ void __launch_bounds__(256, VIDC_SHEAR_BLOCKS_FWD)
+__global__ void __launch_bounds__(256, GW ? VIDC_SHEAR_BLOCKS_FWD : VIDC_SHEAR_BLOCKS_RT)
 warp_rgbd_shear_kernel(const __grid_constant__ FwdArgs a) {
-    static_assert(GW > 0 && GW % 32 == 0, "sheared tiles need a compile-time canvas whose width is a multiple of 32");
+    static_assert(GW % 32 == 0, "sheared tiles need a canvas whose width is a multiple of 32 (GW = 0: runtime geometry)");
     static_assert(ROWS_PER_THREAD == 4 && PATCH_W == 32 && TILE_W == 32 && TILE_H == 32, "32x32 tile, 8 warps x 4 segments");
-    constexpr int W = GW, H = GH;
+    const int W = GW ? GW : a.cam.W, H = GW ? GH : a.cam.H;
     __shared__ __align__(16) float4 tile[32][32];
     const int b = blockIdx.z, lane = threadIdx.x, warp = threadIdx.y;
     const int tileX0 = blockIdx.x * TILE_W, tileY0 = blockIdx.y * TILE_H;
@@ -186,7 +190,7 @@ struct PlanesArgs {
 
 template <int GW, int GH, int C, bool ALONG_Y>
 __device__ __forceinline__ void warp_planes_shear_segments(const PlanesArgs& a, const float* pr, float4 (*tile)[32], int sh_l) {
-    constexpr int W = GW, H = GH;
+    const int W = GW ? GW : a.cam.W, H = GW ? GH : a.cam.H;
     const int b = blockIdx.z, lane = threadIdx.x, warp = threadIdx.y;
     const int tileX0 = blockIdx.x * TILE_W, tileY0 = blockIdx.y * TILE_H;
     const float* Hi = pr + 2;
@@ -237,10 +241,10 @@ __device__ __forceinline__ void warp_planes_shear_segments(const PlanesArgs& a, 
 
 template <int GW, int GH, int C, bool ALONG_Y>
 __device__ __forceinline__ void warp_planes_shear_write_out(const PlanesArgs& a, const float4 (*tile)[32]) {
-    constexpr int W = GW, H = GH;
+    const int W = GW ? GW : a.cam.W, H = GW ? GH : a.cam.H;
     const int b = blockIdx.z, tid = threadIdx.y * 32 + threadIdx.x, row = tid >> 3, c4 = (tid & 7) * 4;
     const int Yo = blockIdx.y * TILE_H + row, Xo = blockIdx.x * TILE_W + c4;
-    if (H % 32 == 0 || Yo < H) {
+    if ((GW && GH % 32 == 0) || Yo < H) {
         float4 px4[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) px4[k] = tile[row][shear_slot<ALONG_Y>(row, c4 + k)];
@@ -253,9 +257,9 @@ __device__ __forceinline__ void warp_planes_shear_write_out(const PlanesArgs& a,
 }
 
 template <int GW, int GH, int C>
-__global__ void __launch_bounds__(256, VIDC_SHEAR_BLOCKS_FWD)
+__global__ void __launch_bounds__(256, GW ? VIDC_SHEAR_BLOCKS_FWD : VIDC_SHEAR_BLOCKS_RT)
 warp_planes_shear_kernel(const __grid_constant__ PlanesArgs a) {
-    static_assert(GW > 0 && GW % 32 == 0 && C >= 1 && C <= 4, "compile-time canvas, 1-4 planes");
+    static_assert(GW % 32 == 0 && C >= 1 && C <= 4, "canvas width a multiple of 32, 1-4 planes");
     static_assert(ROWS_PER_THREAD == 4 && PATCH_W == 32 && TILE_W == 32 && TILE_H == 32, "32x32 tile, 8 warps x 4 segments");
     __shared__ __align__(16) float4 tile[32][32];
     const int b = blockIdx.z, lane = threadIdx.x;
@@ -286,7 +290,7 @@ warp_planes_shear_kernel(const __grid_constant__ PlanesArgs a) {
 // The fourth component of the staging slot carries the optional validity flag.
 template <int GW, int GH, bool NORMALIZE, bool ALONG_Y>
 __device__ __forceinline__ void unwarp_normals_shear_segments(const InvArgs& a, const float* pr, float4 (*tile)[32], int sh_l) {
-    constexpr int W = GW, H = GH;
+    const int W = GW ? GW : a.cam.W, H = GW ? GH : a.cam.H;
     const int b = blockIdx.z, lane = threadIdx.x, warp = threadIdx.y;
     const int tileX0 = blockIdx.x * TILE_W, tileY0 = blockIdx.y * TILE_H;
     const float* Hm = pr;
@@ -333,13 +337,13 @@ __device__ __forceinline__ void unwarp_normals_shear_segments(const InvArgs& a, 
 // columns with 128-bit stores: this form keeps the whole kernel inside 32 registers without spills.)
 template <int GW, int GH, bool ALONG_Y>
 __device__ __forceinline__ void unwarp_normals_shear_write_out(const InvArgs& a, const float4 (*tile)[32]) {
-    constexpr int W = GW, H = GH;
+    const int W = GW ? GW : a.cam.W, H = GW ? GH : a.cam.H;
     const int b = blockIdx.z, tid = threadIdx.y * 32 + threadIdx.x, c2 = (tid & 15) * 2;
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
         const int row = (tid >> 4) + 16 * pass;
         const int Yo = blockIdx.y * TILE_H + row, Xo = blockIdx.x * TILE_W + c2;
-        if (H % 32 == 0 || Yo < H) {
+        if ((GW && GH % 32 == 0) || Yo < H) {
             const float4 za = tile[row][shear_slot<ALONG_Y>(row, c2)], zb = tile[row][shear_slot<ALONG_Y>(row, c2 + 1)];
             float* __restrict__ o = a.z + ((long long)b * a.z_sn + Yo * W + Xo);
             *reinterpret_cast<float2*>(o) = make_float2(za.x, zb.x);
@@ -353,11 +357,11 @@ __device__ __forceinline__ void unwarp_normals_shear_write_out(const InvArgs& a,
 }
 
 template <int GW, int GH, bool NORMALIZE>
-__global__ void __launch_bounds__(256, VIDC_SHEAR_BLOCKS_INV)
+__global__ void __launch_bounds__(256, GW ? VIDC_SHEAR_BLOCKS_INV : VIDC_SHEAR_BLOCKS_RT)
 unwarp_normals_shear_kernel(const __grid_constant__ InvArgs a) {
-    static_assert(GW > 0 && GW % 32 == 0, "sheared tiles need a compile-time canvas whose width is a multiple of 32");
+    static_assert(GW % 32 == 0, "sheared tiles need a canvas whose width is a multiple of 32 (GW = 0: runtime geometry)");
     static_assert(ROWS_PER_THREAD == 4 && PATCH_W == 32 && TILE_W == 32 && TILE_H == 32, "32x32 tile, 8 warps x 4 segments");
-    constexpr int W = GW, H = GH;
+    const int W = GW ? GW : a.cam.W, H = GW ? GH : a.cam.H;
     __shared__ __align__(16) float4 tile[32][32];
     const int b = blockIdx.z, lane = threadIdx.x, warp = threadIdx.y;
     const int tileX0 = blockIdx.x * TILE_W, tileY0 = blockIdx.y * TILE_H;
