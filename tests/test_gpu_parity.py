@@ -259,8 +259,9 @@ print("VARIANT_OK")
 '''
 
 
-@pytest.mark.parametrize("env", [{"VIDC_SHEAR": "0"}, {"VIDC_SHEAR": "1"}, {"VIDC_SHEAR": "2"}, {"VIDC_TMA": "1"}],
-                         ids=["straight-rows", "sheared-forward", "sheared-both", "tma-staged"])
+@pytest.mark.parametrize("env", [{"VIDC_SHEAR": "0"}, {"VIDC_SHEAR": "1"}, {"VIDC_SHEAR": "2"}, {"VIDC_TMA": "1"},
+                                 {"VIDC_TILE_SKIP": "0"}],
+                         ids=["straight-rows", "sheared-forward", "sheared-both", "tma-staged", "no-tile-skip"])
 def test_kernel_variants_match_oracle(cuda_device, oracle_mod, env):
     """Every kernel family behind the fused entry points, each selected by its environment switch in a fresh process:
     straight row segments (VIDC_SHEAR=0), sheared forward rows only (=1), sheared forward + inverse (=2, the default) and
@@ -509,3 +510,31 @@ def test_isolated_nonfinite_coordinate_inside_a_warp(cuda_device, oracle_mod):
     assert np.array_equal(mask.cpu().numpy().reshape(-1), O.validity_mask(oy).reshape(-1))
     assert C.count_bit_mismatches(z.cpu().numpy(), oz) == 0
     assert C.count_bit_mismatches(nhat.cpu().numpy(), ozn) == 0
+
+
+def test_exterior_tile_bitmap_never_drops_a_pixel(cuda_device, oracle_mod):
+    """The forward kernels skip 32x32 canvas tiles that frame_params_tiles_kernel marks as certainly outside the source
+    footprint (a conservative corner test with a margin).  Many frames over the whole roll / pitch range, an all-ones and
+    a random image: every output pixel on the oracle's bits, so no marked tile ever contained a pixel of the footprint."""
+    from oracle import oracle as O
+    for cam_name, B, roll, pitch, seed in (("S1", 192, 89, 75, 31), ("S1", 64, 30, 30, 32), ("S2", 24, 89, 75, 33)):
+        w, o = _mk(cam_name, cuda_device)
+        Hh, Ww = int(w.H), int(w.W)
+        I_g, I_a = C.random_gravity(B, seed=seed, roll_deg=roll, pitch_deg=pitch)
+        rs = np.random.RandomState(seed)
+        I_a[B // 2:] = rs.randn(B - B // 2, 3).astype(np.float32)              # general alignment directions too
+        rgb = np.ones((B, 3, Hh, Ww), np.float32)
+        rgb[B // 3:] = C.random_images(B - B // 3, Hh, Ww, seed=seed)[0]
+        depth = C.random_images(B, Hh, Ww, seed=seed + 1)[1]
+        g, a = _t(I_g, cuda_device), _t(I_a, cuda_device)
+        _, rgb_w, depth_w, mask, cov = w.warp_rgbd(_t(rgb, cuda_device), _t(depth, cuda_device), g, a, with_coverage=True)
+        _, y = w.warp_with_gravity_center_aligned(_t(rgb, cuda_device), g, a)
+        with np.errstate(all="ignore"):
+            _, oy = o.warp_with_gravity_center_aligned(rgb, I_g, I_a)
+            _, oyd = o.warp_with_gravity_center_aligned(depth, I_g, I_a)
+        om = O.validity_mask(oy)
+        assert C.count_bit_mismatches(rgb_w.cpu().numpy(), oy) == 0
+        assert C.count_bit_mismatches(y.cpu().numpy(), oy) == 0
+        assert C.count_bit_mismatches(depth_w.cpu().numpy().reshape(oyd.shape), oyd) == 0
+        assert np.array_equal(mask.cpu().numpy().reshape(-1), om.reshape(-1))
+        assert np.array_equal(cov.cpu().numpy().astype(np.int64), om.reshape(B, -1).sum(1).astype(np.int64))

@@ -66,6 +66,15 @@ __device__ __forceinline__ bool shear_of_tile(float ax, float ay, int lane, int&
     return along_y;
 }
 
+// Exterior-tile bitmap (frame_params_tiles_kernel, kernels_params.cuh): bit t of vidc_frame_params::reserved is set when canvas
+// tile t certainly lies outside the source footprint.  Parameters from any other producer carry zeros there.
+__device__ __forceinline__ bool tile_marked_exterior(const vidc_frame_params* __restrict__ prm) {
+    const unsigned int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    if (tile >= 320u) return false;
+    const unsigned int word = __float_as_uint(__ldg(&prm->reserved[tile >> 5]));
+    return (word >> (tile & 31u)) & 1u;
+}
+
 // ---- forward: RGB (3 planes) + optional depth, mask, coverage -------------------------------------------------------
 template <int GW, int GH, bool HAS_D, bool ALONG_Y>
 __device__ __forceinline__ void warp_rgbd_shear_segments(const FwdArgs& a, const float* pr, float4 (*tile)[32], int sh_l) {
@@ -156,6 +165,20 @@ warp_rgbd_shear_kernel(const __grid_constant__ FwdArgs a) {
     __shared__ __align__(16) float4 tile[32][32];
     const int b = blockIdx.z, lane = threadIdx.x, warp = threadIdx.y;
     const int tileX0 = blockIdx.x * TILE_W, tileY0 = blockIdx.y * TILE_H;
+    if (tile_marked_exterior(a.prm + b)) {                         // CTA-uniform: nothing of the source lands here, all zeros
+        const int tid = warp * 32 + lane, row = tid >> 3, c4 = (tid & 7) * 4;
+        const int Yo = tileY0 + row, Xo = tileX0 + c4;
+        if ((GW && GH % 32 == 0) || Yo < H) {
+            const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            float* __restrict__ o_rgb = a.rgb_o + ((long long)b * a.rgbo_sn + Yo * W + Xo);
+            *reinterpret_cast<float4*>(o_rgb) = z4;
+            *reinterpret_cast<float4*>(o_rgb + W * H) = z4;
+            *reinterpret_cast<float4*>(o_rgb + 2 * W * H) = z4;
+            if (HAS_D) *reinterpret_cast<float4*>(a.dep_o + ((long long)b * a.depo_sn + Yo * W + Xo)) = z4;
+            if (a.mask) *reinterpret_cast<unsigned int*>(a.mask + (((long long)b * H + Yo) * W + Xo)) = 0u;
+        }
+        return;
+    }
     // params: Hinv = floats 18..26, px_min,py_min = 27,28, ikw,ikh = 31,32 -> float4 #4..#8 (floats 16..35)
     float pr[20];
     load_params(a.prm + b, pr, 4, 5);
@@ -264,6 +287,18 @@ warp_planes_shear_kernel(const __grid_constant__ PlanesArgs a) {
     __shared__ __align__(16) float4 tile[32][32];
     const int b = blockIdx.z, lane = threadIdx.x;
     const int tileX0 = blockIdx.x * TILE_W, tileY0 = blockIdx.y * TILE_H;
+    if (tile_marked_exterior(a.prm + b)) {                         // CTA-uniform: all zeros
+        const int W = GW ? GW : a.cam.W, H = GW ? GH : a.cam.H;
+        const int tid = threadIdx.y * 32 + lane, row = tid >> 3, c4 = (tid & 7) * 4;
+        const int Yo = tileY0 + row, Xo = tileX0 + c4;
+        if ((GW && GH % 32 == 0) || Yo < H) {
+            const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            float* __restrict__ o = a.y + ((long long)b * a.y_sn + Yo * W + Xo);
+#pragma unroll
+            for (int c = 0; c < C; ++c) *reinterpret_cast<float4*>(o + c * (W * H)) = z4;
+        }
+        return;
+    }
     float pr[20];
     load_params(a.prm + b, pr, 4, 5);
     int sh_l;
