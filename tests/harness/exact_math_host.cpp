@@ -37,3 +37,15 @@ extern "C" void host_condition_gravity(const float* raw, int B, int rule, float*
 extern "C" void host_mkl_sinf_ha(const float* x, size_t n, float* out) {
     for (size_t i = 0; i < n; ++i) out[i] = vidc::mkl_sinf_ha(x[i]);
 }
+
+// exterior-tile bitmap of the forward kernels (csrc/frame_params.cuh: tile_certainly_exterior), one byte per 32x32 tile
+extern "C" void host_exterior_tiles(const vidc_camera* cam, const float* Ig, const float* Ia, int B, unsigned char* out) {
+    const int tiles_x = (cam->W + 31) / 32, tiles_y = (cam->H + 31) / 32;
+    for (int i = 0; i < B; ++i) {
+        vidc_frame_params p;
+        memset(&p, 0, sizeof p);
+        vidc::frame_params_from_gravity(*cam, Ig + 3 * i, Ia + 3 * i, p);
+        for (int t = 0; t < tiles_x * tiles_y; ++t)
+            out[(size_t)i * tiles_x * tiles_y + t] = vidc::tile_certainly_exterior(p, *cam, t % tiles_x, t / tiles_x) ? 1 : 0;
+    }
+}

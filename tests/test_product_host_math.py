@@ -100,3 +100,38 @@ def test_mkl_sin_restatement_vs_oracle(hlib, oracle_mod):
     hlib.host_mkl_sinf_ha(_p(x), ctypes.c_size_t(x.size), _p(a))
     oracle_mod.lib().vidc_oracle_sinf_array(_p(x), ctypes.c_size_t(x.size), _p(b))
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("cam_name", ["S1", "tiny"])
+def test_exterior_tile_test_is_conservative(hlib, oracle_mod, cam_name):
+    """csrc/frame_params.cuh: tile_certainly_exterior -- the test behind the forward kernels' exterior-tile bitmap -- compiled
+    for the host and checked against the oracle: over random, extreme, edge-case, degenerate and pole-crossing gravity no
+    marked tile may contain a pixel that receives anything from an all-ones source image, and the test must actually
+    mark a good share of the truly exterior tiles (otherwise it is useless)."""
+    from vi_depth_completion_b200._cabi import VidcCamera, lib
+    cam = C.CAMERAS[cam_name]
+    o = oracle_mod.Oracle(*cam)
+    c = VidcCamera()
+    assert lib().vidc_camera_init(*[float(v) for v in cam], ctypes.byref(c)) == 0
+    tiles_x, tiles_y = (o.W + 31) // 32, (o.H + 31) // 32
+    marked = truly = wrong = 0
+    rs = np.random.RandomState(3)
+    sets = [C.random_gravity(40, 1, 30, 30), C.random_gravity(40, 2, 89, 75), C.extreme_roll_gravity(14, 3),
+            C.edge_case_gravity(), C.degenerate_gravity(), C.isolated_nonfinite_gravity()]
+    ga = C.random_gravity(24, 5, 60, 60)
+    sets.append((ga[0], rs.randn(24, 3).astype(np.float32)))                     # general alignment directions
+    for I_g, I_a in sets:
+        B = I_g.shape[0]
+        bits = np.zeros((B, tiles_y, tiles_x), np.uint8)
+        hlib.host_exterior_tiles(ctypes.byref(c), _p(np.ascontiguousarray(I_g)), _p(np.ascontiguousarray(I_a)), B, _p(bits))
+        with np.errstate(all="ignore"):
+            _, y = o.warp_with_gravity_center_aligned(np.ones((B, 1, o.H, o.W), np.float32), I_g, I_a)
+        hit = np.zeros((B, tiles_y * 32, tiles_x * 32), bool)
+        hit[:, :o.H, :o.W] = (y[:, 0] != 0) | np.isnan(y[:, 0])
+        hit_tiles = hit.reshape(B, tiles_y, 32, tiles_x, 32).any(axis=(2, 4))
+        wrong += int((bits.astype(bool) & hit_tiles).sum())
+        marked += int(bits.sum()); truly += int((~hit_tiles).sum())
+    assert wrong == 0
+    print(f"{cam_name}: {marked} of {truly} exterior tiles marked")
+    if cam_name == "S1":                  # 10 x 8 tiles; on the 2 x 2 tiles of the tiny canvas few tiles are exterior at all
+        assert marked > 0.6 * truly > 0

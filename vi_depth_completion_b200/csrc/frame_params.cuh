@@ -100,4 +100,32 @@ VIDC_HD void frame_params_from_gravity(const vidc_camera& cam, const float* g, c
     frame_scale(cam, p.H, p);
 }
 
+// Conservative 'this 32x32 canvas tile lies entirely outside the source footprint' (kernels_params.cuh explains why it is
+// safe; forward warp with input and canvas of the same size).  Not part of any result: it only decides which CTAs may
+// write zeros without computing coordinates.
+VIDC_HD bool tile_certainly_exterior(const vidc_frame_params& p, const vidc_camera& cam, int tx, int ty) {
+    const float Wf = (float)cam.W, Hf = (float)cam.H;
+    const float X[2] = {(float)(tx * 32), fminf((float)(tx * 32 + 31), Wf - 1.0f)};
+    const float Y[2] = {(float)(ty * 32), fminf((float)(ty * 32 + 31), Hf - 1.0f)};
+    float ix_lo = 3.0e38f, ix_hi = -3.0e38f, iy_lo = 3.0e38f, iy_hi = -3.0e38f, s_lo = 3.0e38f, s_hi = -3.0e38f;
+    bool ok = true;
+    for (int c = 0; c < 4; ++c) {
+        const float px = p.ikw * X[c & 1] + p.px_min, py = p.ikh * Y[c >> 1] + p.py_min;
+        const float t0 = p.Hinv[6] * px, t1 = p.Hinv[7] * py;
+        const float s = t0 + t1 + p.Hinv[8];
+        const float u = p.Hinv[0] * px + p.Hinv[1] * py + p.Hinv[2];
+        const float v = p.Hinv[3] * px + p.Hinv[4] * py + p.Hinv[5];
+        ok = ok && fabsf(s) > 1e-3f * (fabsf(t0) + fabsf(t1) + fabsf(p.Hinv[8]));
+        const float ix = ((u / s - cam.cx) * cam.inv_half_w + 1.0f) * Wf * 0.5f - 0.5f;
+        const float iy = ((v / s - cam.cy) * cam.inv_half_h + 1.0f) * Hf * 0.5f - 0.5f;
+        ok = ok && fabsf(ix) < 1e30f && fabsf(iy) < 1e30f;          // also rejects NaN
+        ix_lo = fminf(ix_lo, ix); ix_hi = fmaxf(ix_hi, ix); iy_lo = fminf(iy_lo, iy); iy_hi = fmaxf(iy_hi, iy);
+        s_lo = fminf(s_lo, s); s_hi = fmaxf(s_hi, s);
+    }
+    ok = ok && (s_lo > 0.0f || s_hi < 0.0f);
+    const float mx = 4.0f + 2e-3f * fmaxf(fabsf(ix_lo), fabsf(ix_hi)), my = 4.0f + 2e-3f * fmaxf(fabsf(iy_lo), fabsf(iy_hi));
+    return ok && (ix_hi < -1.0f - mx || ix_lo > Wf + mx || iy_hi < -1.0f - my || iy_lo > Hf + my);
+}
+
+
 }  // namespace vidc

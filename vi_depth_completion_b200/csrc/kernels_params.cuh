@@ -41,31 +41,7 @@ __global__ void frame_params_kernel(vidc_camera cam, const float* __restrict__ I
 // demanded below (|s| > 1e-3 of the sum of its terms' magnitudes) that is < 1e-4 of the coordinate's magnitude plus a
 // fraction of a pixel, at the corners here and at every pixel there.  The margin 4 px + 2e-3 |coordinate| is 20x that.
 // Anything that fails a condition (sign change, ill-conditioned or non-finite corner) is simply not marked.
-__device__ __forceinline__ bool tile_certainly_exterior(const vidc_frame_params& p, const vidc_camera& cam, int tx, int ty) {
-    const float Wf = (float)cam.W, Hf = (float)cam.H;
-    const float X[2] = {(float)(tx * 32), fminf((float)(tx * 32 + 31), Wf - 1.0f)};
-    const float Y[2] = {(float)(ty * 32), fminf((float)(ty * 32 + 31), Hf - 1.0f)};
-    float ix_lo = 3.0e38f, ix_hi = -3.0e38f, iy_lo = 3.0e38f, iy_hi = -3.0e38f, s_lo = 3.0e38f, s_hi = -3.0e38f;
-    bool ok = true;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const float px = p.ikw * X[c & 1] + p.px_min, py = p.ikh * Y[c >> 1] + p.py_min;
-        const float t0 = p.Hinv[6] * px, t1 = p.Hinv[7] * py;
-        const float s = t0 + t1 + p.Hinv[8];
-        const float u = p.Hinv[0] * px + p.Hinv[1] * py + p.Hinv[2];
-        const float v = p.Hinv[3] * px + p.Hinv[4] * py + p.Hinv[5];
-        ok = ok && fabsf(s) > 1e-3f * (fabsf(t0) + fabsf(t1) + fabsf(p.Hinv[8]));
-        const float ix = ((u / s - cam.cx) * cam.inv_half_w + 1.0f) * Wf * 0.5f - 0.5f;
-        const float iy = ((v / s - cam.cy) * cam.inv_half_h + 1.0f) * Hf * 0.5f - 0.5f;
-        ok = ok && fabsf(ix) < 1e30f && fabsf(iy) < 1e30f;          // also rejects NaN
-        ix_lo = fminf(ix_lo, ix); ix_hi = fmaxf(ix_hi, ix); iy_lo = fminf(iy_lo, iy); iy_hi = fmaxf(iy_hi, iy);
-        s_lo = fminf(s_lo, s); s_hi = fmaxf(s_hi, s);
-    }
-    ok = ok && (s_lo > 0.0f || s_hi < 0.0f);
-    const float mx = 4.0f + 2e-3f * fmaxf(fabsf(ix_lo), fabsf(ix_hi)), my = 4.0f + 2e-3f * fmaxf(fabsf(iy_lo), fabsf(iy_hi));
-    return ok && (ix_hi < -1.0f - mx || ix_lo > Wf + mx || iy_hi < -1.0f - my || iy_lo > Hf + my);
-}
-
+// The test itself is vidc::tile_certainly_exterior (frame_params.cuh, host / device: tests/ run it on the CPU).
 __global__ void __launch_bounds__(320) frame_params_tiles_kernel(vidc_camera cam, const float* __restrict__ Ig,
                                                                  const float* __restrict__ Ia, int B,
                                                                  vidc_frame_params* __restrict__ out, float* __restrict__ H_out) {
@@ -84,7 +60,7 @@ __global__ void __launch_bounds__(320) frame_params_tiles_kernel(vidc_camera cam
     }
     __syncthreads();
     const int tiles_x = (cam.W + 31) / 32, tiles_y = (cam.H + 31) / 32, nt = tiles_x * tiles_y;
-    const bool ext = nt <= 320 && t < nt && tile_certainly_exterior(sp, cam, t % tiles_x, t / tiles_x);
+    const bool ext = nt <= 320 && t < nt && vidc::tile_certainly_exterior(sp, cam, t % tiles_x, t / tiles_x);
     const unsigned int bal = __ballot_sync(0xffffffffu, ext);
     float* __restrict__ o = reinterpret_cast<float*>(out + i);
     const float* spf = reinterpret_cast<const float*>(&sp);
