@@ -75,7 +75,9 @@ typedef struct vidc_frame_params {
     float w_max, h_max;    /* :132-133 */
     float fwd_col_major;   /* 1.0 when canvas rows of the forward warp run along source columns (roll beyond ~76 deg): kernels take column-major tiles */
     float inv_col_major;   /* same for the inverse warp */
-    float reserved[11];
+    float reserved[11];    /* [0..9]: bit t set = 32x32 canvas tile t (row-major, <= 320 tiles) certainly lies outside the source
+                              footprint of the forward warp -- written by the forward entry points, zero from every other
+                              producer; [10]: zero */
 } vidc_frame_params;
 
 /* Logical (N, C, H, W) image batch with element strides.  N <= 65535 frames per call (they ride on gridDim.z); one
