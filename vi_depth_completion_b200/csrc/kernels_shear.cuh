@@ -323,7 +323,7 @@ warp_planes_shear_kernel(const __grid_constant__ PlanesArgs a) {
 
 // ---- inverse: camera px -> canvas coords, 3 planes, R^T, renormalisation ------------------------------------------------
 // The fourth component of the staging slot carries the optional validity flag.
-template <int GW, int GH, bool NORMALIZE, bool ALONG_Y>
+template <int GW, int GH, bool NORMALIZE, bool HAS_VALID, bool ALONG_Y>
 __device__ __forceinline__ void unwarp_normals_shear_segments(const InvArgs& a, const float* pr, float4 (*tile)[32], int sh_l) {
     const int W = GW ? GW : a.cam.W, H = GW ? GH : a.cam.H;
     const int b = blockIdx.z, lane = threadIdx.x, warp = threadIdx.y;
@@ -357,20 +357,20 @@ __device__ __forceinline__ void unwarp_normals_shear_segments(const InvArgs& a, 
         const float gx = a.cam.inv_half_w * (cxp - a.cam.cx);
         const float gy = a.cam.inv_half_h * (cyp - a.cam.cy);
         const Pos t = make_pos(unnormalize(gx, Wf), unnormalize(gy, Hf), H, W);
-        const Px3 y = inv_sample_row(in, W, W * H, H, W, t);
+        const Px3 y = HAS_VALID ? inv_sample_row(in, W, W * H, H, W, t) : inv_sample_row_lazy(in, W, W * H, H, W, t);
         // z = C_R_Cg.bmm(y), C_R_Cg = R^T: k-ascending FMA chain from a +0 accumulator (:253)
         float z0 = fmaf(R[6], y.c, fmaf(R[3], y.b, fmaf(R[0], y.a, 0.0f)));
         float z1 = fmaf(R[7], y.c, fmaf(R[4], y.b, fmaf(R[1], y.a, 0.0f)));
         float z2 = fmaf(R[8], y.c, fmaf(R[5], y.b, fmaf(R[2], y.a, 0.0f)));
         if (NORMALIZE) normalize3_rn(z0, z1, z2);                  // surface_normal.py:170
         const int row = ALONG_Y ? lane : S, col = ALONG_Y ? S : lane;
-        tile[row][shear_slot<ALONG_Y>(row, col)] = make_float4(z0, z1, z2, (a.valid && t.touch) ? 1.0f : 0.0f);
+        tile[row][shear_slot<ALONG_Y>(row, col)] = make_float4(z0, z1, z2, (HAS_VALID && t.touch) ? 1.0f : 0.0f);
     }
 }
 
 // Two passes of (row, 2 consecutive columns) per thread, 64-bit row stores per plane.  (Measured against one pass of four
 // columns with 128-bit stores: this form keeps the whole kernel inside 32 registers without spills.)
-template <int GW, int GH, bool ALONG_Y>
+template <int GW, int GH, bool HAS_VALID, bool ALONG_Y>
 __device__ __forceinline__ void unwarp_normals_shear_write_out(const InvArgs& a, const float4 (*tile)[32]) {
     const int W = GW ? GW : a.cam.W, H = GW ? GH : a.cam.H;
     const int b = blockIdx.z, tid = threadIdx.y * 32 + threadIdx.x, c2 = (tid & 15) * 2;
@@ -384,14 +384,15 @@ __device__ __forceinline__ void unwarp_normals_shear_write_out(const InvArgs& a,
             *reinterpret_cast<float2*>(o) = make_float2(za.x, zb.x);
             *reinterpret_cast<float2*>(o + W * H) = make_float2(za.y, zb.y);
             *reinterpret_cast<float2*>(o + 2 * W * H) = make_float2(za.z, zb.z);
-            if (a.valid)
+            if (HAS_VALID)
                 *reinterpret_cast<unsigned short*>(a.valid + (((long long)b * H + Yo) * W + Xo)) =
                     (unsigned short)((za.w != 0.0f ? 1u : 0u) | (zb.w != 0.0f ? 0x100u : 0u));
         }
     }
 }
 
-template <int GW, int GH, bool NORMALIZE>
+// HAS_VALID = false (no validity output requested) drops the `touch` test from the all-interior fast path
+template <int GW, int GH, bool NORMALIZE, bool HAS_VALID>
 __global__ void __launch_bounds__(256, GW ? VIDC_SHEAR_BLOCKS_INV : VIDC_SHEAR_BLOCKS_RT)
 unwarp_normals_shear_kernel(const __grid_constant__ InvArgs a) {
     static_assert(GW % 32 == 0, "sheared tiles need a canvas whose width is a multiple of 32 (GW = 0: runtime geometry)");
@@ -412,14 +413,14 @@ unwarp_normals_shear_kernel(const __grid_constant__ InvArgs a) {
         along_y = shear_of_tile(Hm[3] * sc - vc * Hm[6], Hm[4] * sc - vc * Hm[7], lane, sh_l);
     }
     if (along_y) {                                                 // CTA-uniform; the common orientation stays straight-line
-        unwarp_normals_shear_segments<GW, GH, NORMALIZE, true>(a, pr, tile, sh_l);
+        unwarp_normals_shear_segments<GW, GH, NORMALIZE, HAS_VALID, true>(a, pr, tile, sh_l);
         __syncthreads();
-        unwarp_normals_shear_write_out<GW, GH, true>(a, tile);
+        unwarp_normals_shear_write_out<GW, GH, HAS_VALID, true>(a, tile);
         return;
     }
-    unwarp_normals_shear_segments<GW, GH, NORMALIZE, false>(a, pr, tile, sh_l);
+    unwarp_normals_shear_segments<GW, GH, NORMALIZE, HAS_VALID, false>(a, pr, tile, sh_l);
     __syncthreads();
-    unwarp_normals_shear_write_out<GW, GH, false>(a, tile);
+    unwarp_normals_shear_write_out<GW, GH, HAS_VALID, false>(a, tile);
 }
 
 }  // namespace vidc_k
