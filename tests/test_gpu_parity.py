@@ -538,3 +538,47 @@ def test_exterior_tile_bitmap_never_drops_a_pixel(cuda_device, oracle_mod):
         assert C.count_bit_mismatches(depth_w.cpu().numpy().reshape(oyd.shape), oyd) == 0
         assert np.array_equal(mask.cpu().numpy().reshape(-1), om.reshape(-1))
         assert np.array_equal(cov.cpu().numpy().astype(np.int64), om.reshape(B, -1).sum(1).astype(np.int64))
+
+
+def test_random_cameras_match_oracle(cuda_device, oracle_mod):
+    """Fuzz over intrinsics: random canvas sizes (every third one with a width that is a multiple of 32, which takes the
+    runtime-geometry sheared kernels; the others take the straight-row runtime-geometry kernels) and moderate / extreme /
+    arbitrary gravity.  Fused and reference-shaped calls on the oracle's bits."""
+    from oracle import oracle as O
+    from vi_depth_completion_b200.warping_2dof_alignment import Warping2DOFAlignment
+    rs = np.random.RandomState(77)
+    for case in range(18):
+        fx = float(rs.uniform(40, 500)); fy = float(fx * rs.uniform(0.9, 1.1))
+        cx = float(rs.uniform(20, 180)); cy = float(rs.uniform(15, 120))
+        if case % 3 == 0:
+            cx = 16.0 * int(rs.randint(2, 12)) - 0.3                          # W = ceil(2 cx) = 32 k
+        w, o = Warping2DOFAlignment(fx=fx, fy=fy, cx=cx, cy=cy), oracle_mod.Oracle(fx, fy, cx, cy)
+        assert (int(w.W), int(w.H)) == (o.W, o.H)
+        B, kind = 4, case % 4
+        if kind == 0:
+            I_g, I_a = C.random_gravity(B, rs.randint(1 << 30), 30, 30)
+        elif kind == 1:
+            I_g, I_a = C.random_gravity(B, rs.randint(1 << 30), 89, 80)
+        elif kind == 2:
+            I_g, I_a = rs.randn(B, 3).astype(np.float32), rs.randn(B, 3).astype(np.float32)
+        else:
+            I_g, I_a = C.random_gravity(B, rs.randint(1 << 30), 60, 60)
+            I_g = (I_g * rs.uniform(0.1, 10, (B, 1))).astype(np.float32)
+        rgb, depth, nrm = C.random_images(B, o.H, o.W, rs.randint(1 << 30))
+        g, a = _t(I_g, cuda_device), _t(I_a, cuda_device)
+        _, rgb_w, depth_w, mask = w.warp_rgbd(_t(rgb, cuda_device), _t(depth, cuda_device), g, a)
+        _, y = w.warp_with_gravity_center_aligned(_t(rgb, cuda_device), g, a)
+        _, z = w.inverse_warp_normal_image_with_gravity_center_aligned(_t(nrm, cuda_device), g, a)
+        _, nhat = w.unwarp_normals(_t(nrm, cuda_device), g, a)
+        with np.errstate(all="ignore"):
+            _, oy = o.warp_with_gravity_center_aligned(rgb, I_g, I_a)
+            _, oyd = o.warp_with_gravity_center_aligned(depth, I_g, I_a)
+            _, oz = o.inverse_warp_normal_image_with_gravity_center_aligned(nrm, I_g, I_a)
+            ozn = O.normalize(oz)
+        tag = (case, fx, fy, cx, cy, o.W, o.H)
+        assert C.count_bit_mismatches(rgb_w.cpu().numpy(), oy) == 0, tag
+        assert C.count_bit_mismatches(y.cpu().numpy(), oy) == 0, tag
+        assert C.count_bit_mismatches(depth_w.cpu().numpy().reshape(oyd.shape), oyd) == 0, tag
+        assert np.array_equal(mask.cpu().numpy().reshape(-1), O.validity_mask(oy).reshape(-1)), tag
+        assert C.count_bit_mismatches(z.cpu().numpy(), oz) == 0, tag
+        assert C.count_bit_mismatches(nhat.cpu().numpy(), ozn) == 0, tag
