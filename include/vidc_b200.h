@@ -49,7 +49,9 @@ typedef enum vidc_status {
 
 typedef enum vidc_interp {
     VIDC_BILINEAR = 0, /* interp_mode='bilinear' (:108) */
-    VIDC_NEAREST = 1   /* interp_mode='nearest'             */
+    VIDC_NEAREST = 1,  /* interp_mode='nearest'             */
+    VIDC_BICUBIC = 2   /* interp_mode='bicubic' (valid in F.grid_sample, never used by the reference's callers):
+                          vidc_warp_forward and vidc_warp_normals_forward only, generic kernel, no backward */
 } vidc_interp;
 
 /* Camera constants of Warping2DOFAlignment.__init__ (:6-24).  Plain host struct. */

@@ -8,6 +8,7 @@ What is frozen
   golden_tiny.npz   64x48 camera, 12 edge-case + 6 random frames: every intermediate and output IN FULL
                     (H, R, Hinv, both sampler grids, warped RGB, warped depth bilinear / nearest, un-normalised
                     and normalised un-warped normals, validity mask, nearest pyramid masks, loss statistics).
+  golden_tiny_bicubic.npz  64x48, interp_mode='bicubic' outputs IN FULL
   golden_tiny_special.npz  64x48, signed zeros / denormals / inf / NaN inputs: every output IN FULL
   golden_S1/S2/S3.npz  full-resolution configs of SURVEY.md section 8(d): parameters in full, and for the
                     large tensors a SHA-256 of the raw fp32 bytes plus 4096 sampled values (bit-exact check
@@ -223,6 +224,24 @@ def special_values_golden():
             "y_depth_nearest": ydn.numpy(), "z": z.numpy(), "zn": zn.numpy(), "mask": mask.numpy().astype(np.uint8)}
 
 
+def bicubic_golden():
+    """interp_mode='bicubic' through the reference (valid in F.grid_sample, never used by the reference's callers): the 64x48
+    camera, edge-case + random gravity, RGB and the 3-D depth path, all outputs in full."""
+    Wref = load_reference_class("cpu")
+    fx, fy, cx, cy = C.CAMERAS["tiny"]
+    w = Wref(fx=fx, fy=fy, cx=cx, cy=cy)
+    eg, ea = C.edge_case_gravity()
+    rg, ra = C.random_gravity(6, seed=4321, roll_deg=60, pitch_deg=45)
+    I_g, I_a = np.concatenate([eg, rg]), np.concatenate([ea, ra])
+    B, Hh, Ww = I_g.shape[0], int(w.H), int(w.W)
+    rgb, depth, _ = C.random_images(B, Hh, Ww, seed=7)
+    g, a = torch.from_numpy(I_g), torch.from_numpy(I_a)
+    with torch.no_grad():
+        _, y = w.warp_with_gravity_center_aligned(torch.from_numpy(rgb), g, a, interp_mode="bicubic")
+        _, yd = w.warp_with_gravity_center_aligned(torch.from_numpy(depth), g, a, interp_mode="bicubic")
+    return {"I_g": I_g, "I_a": I_a, "seed": np.int64(7), "y_rgb": y.numpy(), "y_depth": yd.numpy()}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     # tiny: edge cases + random, everything in full
@@ -240,6 +259,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "golden_tiny_backward.npz"), **backward_golden())
     np.savez_compressed(os.path.join(OUT, "golden_rasterize.npz"), **rasterize_golden())
     np.savez_compressed(os.path.join(OUT, "golden_tiny_special.npz"), **special_values_golden())
+    np.savez_compressed(os.path.join(OUT, "golden_tiny_bicubic.npz"), **bicubic_golden())
     raw = gravity_cases()
     azure, scannet = reference_gravity_rules()
     ga = [azure(r) for r in raw]; gs = [scannet(r) for r in raw]

@@ -17,6 +17,9 @@ _LIB_PATH = os.path.join(_HERE, "libwarp_oracle.so")
 _lib = None
 
 
+_MODES = {"bilinear": 0, "nearest": 1, "bicubic": 2}      # vidc_oracle_grid_sample mode codes
+
+
 class OracleCamera(ctypes.Structure):
     _fields_ = [
         ("W", ctypes.c_int32), ("H", ctypes.c_int32),
@@ -93,7 +96,7 @@ class Oracle:
         B, C, Hin, Win = x.shape
         Ho, Wo = grid.shape[1:3]
         out = np.empty((B, C, Ho, Wo), np.float32)
-        lib().vidc_oracle_grid_sample(_p(x), B, C, Hin, Win, _p(grid), Ho, Wo, 0 if mode == "bilinear" else 1, _p(out))
+        lib().vidc_oracle_grid_sample(_p(x), B, C, Hin, Win, _p(grid), Ho, Wo, _MODES[mode], _p(out))
         return out
 
     # ref :108-156
@@ -107,7 +110,7 @@ class Oracle:
         H = np.empty((B, 3, 3), np.float32)
         y = np.empty((B, C, self.H, self.W), np.float32)
         lib().vidc_oracle_warp_forward(ctypes.byref(self.cam), _p(x), B, C, Hin, Win, _p(I_g), _p(I_a),
-                                       0 if interp_mode == "bilinear" else 1, _p(H), _p(y))
+                                       _MODES[interp_mode], _p(H), _p(y))
         return H, (y[:, 0] if squeeze else y)
 
     # ref :216-255

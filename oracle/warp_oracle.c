@@ -299,6 +299,20 @@ static inline float safe_downgrade(float x)
     return x;
 }
 
+/* cubic convolution coefficients for the taps at -1, 0, +1, +2 (ATen get_cubic_upsample_coefficients, A = -0.75) */
+static void bicubic_coefficients(float t, float c[4])
+{
+    const float A = -0.75f;
+    float x = t + 1.0f;
+    c[0] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
+    x = t;
+    c[1] = fmaf(fmaf(A + 2.0f, x, -(A + 3.0f)) * x, x, 1.0f);
+    x = 1.0f - t;
+    c[2] = fmaf(fmaf(A + 2.0f, x, -(A + 3.0f)) * x, x, 1.0f);
+    x = 2.0f - t;
+    c[3] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
+}
+
 API void vidc_oracle_grid_sample(const float *x, int B, int C, int Hin, int Win,
                                  const float *grid, int Hout, int Wout, int mode, float *out)
 {
@@ -332,6 +346,40 @@ API void vidc_oracle_grid_sample(const float *x, int B, int C, int Hin, int Win,
                         acc = fmaf(v_ne, w_ne, acc);
                         acc = fmaf(v_sw, w_sw, acc);
                         acc = fmaf(v_se, w_se, acc);
+                        out[((size_t)b * C + c) * Hout * Wout + opix] = acc;
+                    }
+                } else if (mode == 2) {
+                    /* bicubic (A = -0.75), ATen GridSamplerKernel.cpp / UpSample.h as this torch build rounds it (found by
+                       search against F.grid_sample on CPU, 0 mismatches): coordinates are NOT clipped before the weights
+                       (a non-finite coordinate gives NaN weights, hence NaN, on the CPU and the CUDA build alike);
+                       conv2(x) = ((A x - 5A) x + 8A) x - 4A with every operation rounded,
+                       conv1(x) = fma(fma(A + 2, x, -(A + 3)) * x, x, 1);
+                       row = (fma(c0, v0, c1 v1) + c2 v2) + c3 v3;  result = fma chain over the four rows from cy0 * row0. */
+                    const float rx = unnormalize(g[0], Win), ry = unnormalize(g[1], Hin);
+                    const float x0f = floorf(rx), y0f = floorf(ry);
+                    const float tx = rx - x0f, ty = ry - y0f;
+                    float cx[4], cy[4];
+                    bicubic_coefficients(tx, cx);
+                    bicubic_coefficients(ty, cy);
+                    for (int c = 0; c < C; ++c) {
+                        const float *p = x + ((size_t)b * C + c) * Hin * Win;
+                        float rows[4];
+                        for (int i = 0; i < 4; ++i) {
+                            float v[4];
+                            for (int j = 0; j < 4; ++j) {
+                                const float xf = safe_downgrade(x0f + (float)(j - 1)), yf = safe_downgrade(y0f + (float)(i - 1));
+                                const int xi = (int)xf, yi = (int)yf;
+                                v[j] = (xi >= 0 && xi < Win && yi >= 0 && yi < Hin) ? p[(size_t)yi * Win + xi] : 0.0f;
+                            }
+                            float acc = fmaf(cx[0], v[0], cx[1] * v[1]);
+                            acc = acc + cx[2] * v[2];
+                            acc = acc + cx[3] * v[3];
+                            rows[i] = acc;
+                        }
+                        float acc = cy[0] * rows[0];
+                        acc = fmaf(cy[1], rows[1], acc);
+                        acc = fmaf(cy[2], rows[2], acc);
+                        acc = fmaf(cy[3], rows[3], acc);
                         out[((size_t)b * C + c) * Hout * Wout + opix] = acc;
                     }
                 } else {

@@ -129,3 +129,17 @@ def test_oracle_matches_reference_special_values(oracle_mod):
     assert (np.signbit(g["y_rgb"]) & (g["y_rgb"] == 0)).sum() > 100
     assert (np.signbit(g["z"]) & (g["z"] == 0)).sum() == 0
     assert np.isnan(g["zn"]).sum() > 100 and np.isnan(g["y_rgb"]).sum() > 10
+
+
+def test_oracle_bicubic_matches_reference(oracle_mod):
+    """interp_mode='bicubic' (golden_tiny_bicubic.npz from the executed reference): RGB and the 3-D depth path, bit for bit."""
+    g = _load("tiny_bicubic")
+    fx, fy, cx, cy = C.CAMERAS["tiny"]
+    o = oracle_mod.Oracle(fx, fy, cx, cy)
+    I_g, I_a = g["I_g"], g["I_a"]
+    rgb, depth, _ = C.random_images(I_g.shape[0], o.H, o.W, int(g["seed"]))
+    with np.errstate(all="ignore"):
+        _, y = o.warp_with_gravity_center_aligned(rgb, I_g, I_a, interp_mode="bicubic")
+        _, yd = o.warp_with_gravity_center_aligned(depth, I_g, I_a, interp_mode="bicubic")
+    assert C.count_bit_mismatches(y, g["y_rgb"]) == 0
+    assert C.count_bit_mismatches(yd, g["y_depth"].reshape(yd.shape)) == 0

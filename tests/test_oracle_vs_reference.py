@@ -187,3 +187,24 @@ def test_random_cameras_against_live_reference(oracle_mod):
             assert not (diff & ~pole).any(), (case, fx, fy, cx, cy)
             poles += int(pole.any(axis=1).sum())
     assert poles < 200                                              # isolated pixels (whole non-finite frames excluded above by kind)
+
+
+def test_bicubic_matches_live_reference(oracle_mod):
+    """interp_mode='bicubic' at 320x240 against the executed reference, including special values and degenerate gravity
+    (non-finite coordinates give NaN in both builds of ATen for this mode, so there is no divergence to carve out)."""
+    import torch
+    from oracle.ref_loader import load_reference_class
+    warnings.filterwarnings("ignore")
+    Wref = load_reference_class("cpu")
+    fx, fy, cx, cy = C.CAMERAS["S1"]
+    w, o = Wref(fx=fx, fy=fy, cx=cx, cy=cy), oracle_mod.Oracle(fx, fy, cx, cy)
+    cases = [(C.random_gravity(6, 3, 60, 45), C.random_images(6, o.H, o.W, 5)[0]),
+             (C.extreme_roll_gravity(7, 2), C.random_images(7, o.H, o.W, 6)[0]),
+             (C.special_value_gravity(4), C.special_value_images(4, o.H, o.W, 21)[0]),
+             (C.degenerate_gravity(), C.random_images(C.degenerate_gravity()[0].shape[0], o.H, o.W, 3)[0])]
+    for (I_g, I_a), img in cases:
+        with np.errstate(all="ignore"):
+            _, y = w.warp_with_gravity_center_aligned(torch.from_numpy(img), torch.from_numpy(I_g), torch.from_numpy(I_a),
+                                                      interp_mode="bicubic")
+            _, oy = o.warp_with_gravity_center_aligned(img, I_g, I_a, interp_mode="bicubic")
+        assert C.count_bit_mismatches(y.numpy(), oy) == 0

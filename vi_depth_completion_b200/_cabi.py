@@ -16,6 +16,7 @@ VIDC_ERR_CUDA = -3
 VIDC_ERR_NO_DEVICE = -4
 VIDC_BILINEAR = 0
 VIDC_NEAREST = 1
+VIDC_BICUBIC = 2
 
 c_f32p = ctypes.c_void_p
 

@@ -80,6 +80,56 @@ __device__ __forceinline__ float sample_nearest(const float* __restrict__ plane,
     return in ? __ldg(plane + yn * sh + xn * sw) : 0.0f;
 }
 
+// ---- bicubic (interp_mode='bicubic', A = -0.75): ATen's cubic convolution as torch 2.11 rounds it on CPU (oracle/warp_oracle.c,
+// pinned bit-for-bit against F.grid_sample).  The weights come from the UNCLIPPED coordinate -- a non-finite coordinate gives
+// NaN weights and a NaN result in both builds of ATen -- while each tap coordinate goes through safe_downgrade_to_int_range.
+__device__ __forceinline__ void bicubic_coefficients(float t, float c[4]) {
+    const float A = -0.75f;
+    float x = t + 1.0f;
+    c[0] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
+    x = t;
+    c[1] = fmaf(fmaf(A + 2.0f, x, -(A + 3.0f)) * x, x, 1.0f);
+    x = 1.0f - t;
+    c[2] = fmaf(fmaf(A + 2.0f, x, -(A + 3.0f)) * x, x, 1.0f);
+    x = 2.0f - t;
+    c[3] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
+}
+struct CubicTaps {
+    float cx[4], cy[4];
+    int xi[4], yi[4];          // tap coordinates, already range-checked: -1 = out of bounds
+};
+__device__ __forceinline__ CubicTaps bicubic_taps(float rx, float ry, int Hin, int Win) {
+    CubicTaps t;
+    const float x0f = floorf(rx), y0f = floorf(ry);
+    bicubic_coefficients(rx - x0f, t.cx);
+    bicubic_coefficients(ry - y0f, t.cy);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int xk = (int)safe_coord(x0f + (float)(k - 1)), yk = (int)safe_coord(y0f + (float)(k - 1));
+        t.xi[k] = ((unsigned)xk < (unsigned)Win) ? xk : -1;
+        t.yi[k] = ((unsigned)yk < (unsigned)Hin) ? yk : -1;
+    }
+    return t;
+}
+__device__ __forceinline__ float sample_bicubic(const float* __restrict__ plane, const CubicTaps& t, int sh, int sw) {
+    float rows[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (t.yi[i] >= 0 && t.xi[j] >= 0) ? __ldg(plane + t.yi[i] * sh + t.xi[j] * sw) : 0.0f;
+        float acc = fmaf(t.cx[0], v[0], t.cx[1] * v[1]);          // ((c0 v0 + c1 v1) + c2 v2) + c3 v3, first add contracted
+        acc = acc + t.cx[2] * v[2];
+        acc = acc + t.cx[3] * v[3];
+        rows[i] = acc;
+    }
+    float acc = t.cy[0] * rows[0];                                // FMA chain over the four rows
+    acc = fmaf(t.cy[1], rows[1], acc);
+    acc = fmaf(t.cy[2], rows[2], acc);
+    acc = fmaf(t.cy[3], rows[3], acc);
+    return acc;
+}
+
 // canvas pixel (X, Y) -> source pixel coordinates of the input image (ref :142-150 + ATen unnormalise)
 __device__ __forceinline__ void forward_coords(const float* __restrict__ Hi, float px_min, float py_min,
                                                float ikw, float ikh, const CamConst& cam, float X, float Y,
@@ -95,6 +145,19 @@ __device__ __forceinline__ void forward_coords(const float* __restrict__ Hi, flo
     const float gy = cam.inv_half_h * (sy - cam.cy);                       // :150
     ix = safe_coord(unnormalize(gx, Win));
     iy = safe_coord(unnormalize(gy, Hin));
+}
+// the same without the range clip (bicubic weights use the raw coordinate)
+__device__ __forceinline__ void forward_coords_raw(const float* __restrict__ Hi, float px_min, float py_min,
+                                                   float ikw, float ikh, const CamConst& cam, float X, float Y,
+                                                   float Win, float Hin, float& ix, float& iy) {
+    const float px = ikw * X + px_min;
+    const float py = ikh * Y + py_min;
+    const float u = fmaf(Hi[1], py, Hi[0] * px) + Hi[2];
+    const float v = fmaf(Hi[4], py, Hi[3] * px) + Hi[5];
+    const float s = fmaf(Hi[7], py, Hi[6] * px) + Hi[8];
+    const float sx = u / s, sy = v / s;
+    ix = unnormalize(cam.inv_half_w * (sx - cam.cx), Win);
+    iy = unnormalize(cam.inv_half_h * (sy - cam.cy), Hin);
 }
 
 // camera pixel (X, Y) -> canvas pixel coordinates (ref :242-249 + ATen unnormalise)

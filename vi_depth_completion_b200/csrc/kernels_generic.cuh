@@ -35,6 +35,12 @@ warp_forward_kernel(const vidc_frame_params* __restrict__ prm, CamConst cam,
                 const Taps t = bilinear_taps(ix, iy, a.h, a.w, a.sh, a.sw);
 #pragma unroll
                 for (int c = 0; c < C_A; ++c) out_a[c] = sample_bilinear(base + c * a.sc, t);
+            } else if (mode_a == VIDC_BICUBIC) {
+                float rx, ry;
+                forward_coords_raw(Hi, px_min, py_min, ikw, ikh, cam, (float)X, (float)Y, (float)a.w, (float)a.h, rx, ry);
+                const CubicTaps t = bicubic_taps(rx, ry, a.h, a.w);
+#pragma unroll
+                for (int c = 0; c < C_A; ++c) out_a[c] = sample_bicubic(base + c * a.sc, t, a.sh, a.sw);
             } else {
 #pragma unroll
                 for (int c = 0; c < C_A; ++c) out_a[c] = sample_nearest(base + c * a.sc, ix, iy, a.h, a.w, a.sh, a.sw);

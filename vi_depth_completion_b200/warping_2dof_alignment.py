@@ -104,15 +104,19 @@ def _attach(x, out, warper=None, g=None, a=None, inverse=False, mode=0):
     return out
 
 
-def _check_interp_mode(interp_mode):
+_MODES = {"bilinear": _cabi.VIDC_BILINEAR, "nearest": _cabi.VIDC_NEAREST, "bicubic": _cabi.VIDC_BICUBIC}
+
+
+def _check_interp_mode(interp_mode, allow_bicubic=False):
     """F.grid_sample's own check (the reference forwards interp_mode to it, :150): ValueError for an unknown mode.
     'bicubic' is valid there but never used by the reference's callers (surface_normal.py:148-169 pass 'bilinear' /
-    'nearest'); it is not implemented here and says so instead of silently sampling differently."""
-    if interp_mode in ("bilinear", "nearest"):
-        return
+    'nearest'): the two reference-shaped forward methods support it (generic kernel, forward only); the fused entry points
+    say that they do not instead of silently sampling differently.  Returns the C ABI's mode code."""
+    if interp_mode in ("bilinear", "nearest") or (interp_mode == "bicubic" and allow_bicubic):
+        return _MODES[interp_mode]
     if interp_mode == "bicubic":
-        raise NotImplementedError("interp_mode='bicubic' is not implemented by the B200 path (the reference only calls "
-                                  "'bilinear' and 'nearest')")
+        raise NotImplementedError("depth_mode='bicubic' is not implemented by the fused entry points; use "
+                                  "warp_with_gravity_center_aligned(..., interp_mode='bicubic')")
     raise ValueError("nn.functional.grid_sample(): expected mode to be 'bilinear', 'nearest' or 'bicubic', "
                      f"but got: '{interp_mode}'")
 
@@ -208,7 +212,7 @@ class Warping2DOFAlignment:
             flag_fix_return = True
         if x.dim() != 4:
             raise RuntimeError(f"x: expected a 3-D or 4-D tensor, got {x.dim()}-D")
-        _check_interp_mode(interp_mode)
+        mode = _check_interp_mode(interp_mode, allow_bicubic=True)
         device = x.device
         g, a = _gravity(I_g, I_a, device)
         y = self._empty_like_canvas(x)
@@ -216,10 +220,10 @@ class Warping2DOFAlignment:
         xi, yi = _image(x), _image(y)
         with torch.cuda.device(device):
             check(lib().vidc_warp_forward(ctypes.byref(self._cam), ctypes.byref(xi), g.data_ptr(), a.data_ptr(), g.shape[0],
-                                          _cabi.VIDC_BILINEAR if interp_mode == "bilinear" else _cabi.VIDC_NEAREST,
-                                          self._params_ws(g.shape[0], device).data_ptr(), Cg_H_C.data_ptr(),
+                                          mode, self._params_ws(g.shape[0], device).data_ptr(), Cg_H_C.data_ptr(),
                                           ctypes.byref(yi), _stream_ptr(device)))
-        y = _attach(x, y, self, g, a, False, _cabi.VIDC_BILINEAR if interp_mode == "bilinear" else _cabi.VIDC_NEAREST)
+        # the scatter kernel of vidc_warp_backward covers bilinear and nearest; bicubic is forward-only
+        y = _attach(x, y) if mode == _cabi.VIDC_BICUBIC else _attach(x, y, self, g, a, False, mode)
         if flag_fix_return:                                     # :153-154
             return Cg_H_C, y.view(x.shape[0], y.shape[2], y.shape[3])
         return Cg_H_C, y
@@ -267,7 +271,7 @@ class Warping2DOFAlignment:
         _require_cuda_f32(x, "x")
         if x.dim() != 4 or x.shape[1] != 3:
             raise RuntimeError("x: expected (B,3,H,W)")
-        _check_interp_mode(interp_mode)
+        mode = _check_interp_mode(interp_mode, allow_bicubic=True)
         device = x.device
         g, a = _gravity(I_g, I_a, device)
         z = self._empty_like_canvas(x)
@@ -275,8 +279,7 @@ class Warping2DOFAlignment:
         xi, zi = _image(x), _image(z)
         with torch.cuda.device(device):
             check(lib().vidc_warp_normals_forward(ctypes.byref(self._cam), ctypes.byref(xi), g.data_ptr(), a.data_ptr(),
-                                                  g.shape[0],
-                                                  _cabi.VIDC_BILINEAR if interp_mode == "bilinear" else _cabi.VIDC_NEAREST,
+                                                  g.shape[0], mode,
                                                   self._params_ws(g.shape[0], device).data_ptr(), Cg_H_C.data_ptr(),
                                                   ctypes.byref(zi), _stream_ptr(device)))
         return Cg_H_C, _attach(x, z)
