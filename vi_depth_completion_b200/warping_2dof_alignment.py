@@ -11,7 +11,8 @@ Differences from the reference that are deliberate:
   * the device follows the inputs (the reference pins 'cuda:0', :7);
   * nothing synchronises with the host (the reference reads dozens of device scalars per frame);
   * any canvas size works (the reference hard-codes 240*320 staging buffers, :121-122);
-  * forward only: tensors that require grad raise NotImplementedError in backward;
+  * gradients: the two reference-shaped methods are differentiable w.r.t. the image (vidc_warp_backward, bilinear /
+    nearest); the fused entry points and interp_mode='bicubic' are forward-only and raise NotImplementedError in backward;
   * there is NO CPU / PyTorch fallback: CPU tensors raise RuntimeError.
 """
 import ctypes
