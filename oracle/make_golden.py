@@ -8,6 +8,7 @@ What is frozen
   golden_tiny.npz   64x48 camera, 12 edge-case + 6 random frames: every intermediate and output IN FULL
                     (H, R, Hinv, both sampler grids, warped RGB, warped depth bilinear / nearest, un-normalised
                     and normalised un-warped normals, validity mask, nearest pyramid masks, loss statistics).
+  golden_demo.npz   BASELINE config 1: the eight demo frames' real gravity + klt tracks through loader code and warper
   golden_tiny_bicubic.npz  64x48, interp_mode='bicubic' outputs IN FULL
   golden_tiny_special.npz  64x48, signed zeros / denormals / inf / NaN inputs: every output IN FULL
   golden_S1/S2/S3.npz  full-resolution configs of SURVEY.md section 8(d): parameters in full, and for the
@@ -242,6 +243,44 @@ def bicubic_golden():
     return {"I_g": I_g, "I_a": I_a, "seed": np.int64(7), "y_rgb": y.numpy(), "y_depth": yd.numpy()}
 
 
+def demo_golden():
+    """BASELINE config 1 without the PNGs: the eight demo_dataset frames' REAL gravity files and klt track files through the
+    reference's own loader code (gravity conditioning dataset.py:473-483, rasterisation :496-510) and warper (S1 intrinsics,
+    main.py:243), with seeded smooth synthetic RGB standing in for the colour images and seeded random normals for the
+    CNN output.  Small inputs in full, the large outputs as SHA-256 + 4096 samples."""
+    Wref = load_reference_class("cpu")
+    fx, fy, cx, cy = C.CAMERAS["S1"]
+    w = Wref(fx=fx, fy=fy, cx=cx, cy=cy)
+    gdir = os.path.join(REF_ROOT, "demo_dataset", "gravity")
+    raw = np.stack([np.loadtxt(os.path.join(gdir, f)).astype(np.float32) for f in sorted(os.listdir(gdir))])   # dataset.py:472
+    azure, _ = reference_gravity_rules()
+    cond = [azure(r) for r in raw]
+    I_g, I_a = np.stack([c[0] for c in cond]), np.stack([c[1] for c in cond])
+    ras = rasterize_golden()
+    tracks, counts, depth = ras["tracks"][-8:], ras["counts"][-8:], ras["depth"][-8:]          # the eight demo track files
+    B, Hh, Ww = 8, int(w.H), int(w.W)
+    rgb = C.smooth_images(B, Hh, Ww, seed=11)
+    normals = C.random_images(B, Hh, Ww, seed=12)[2]
+    g, a = torch.from_numpy(I_g), torch.from_numpy(I_a)
+    with torch.no_grad():
+        H, y = w.warp_with_gravity_center_aligned(torch.from_numpy(rgb), g, a)
+        _, yd = w.warp_with_gravity_center_aligned(torch.from_numpy(depth[:, 0]), g, a)
+        _, ydn = w.warp_with_gravity_center_aligned(torch.from_numpy(depth[:, 0]), g, a, interp_mode="nearest")
+        mask = (y[:, 0:1] + y[:, 1:2] + y[:, 2:3] > 1e-2)
+        _, z = w.inverse_warp_normal_image_with_gravity_center_aligned(torch.from_numpy(normals), g, a)
+        zn = F.normalize(z, dim=1)
+    out = {"raw_gravity": raw, "I_g": I_g, "I_a": I_a, "tracks": tracks, "counts": counts, "fc": ras["fc"], "cc": ras["cc"],
+           "Hm": H.numpy(), "rgb_seed": np.int64(11), "normals_seed": np.int64(12),
+           "valid_fraction": np.float64(mask.float().mean())}
+    for k, v in {"depth": depth, "y_rgb": y.numpy(), "y_depth": yd.numpy(), "y_depth_nearest": ydn.numpy(),
+                 "mask": mask.numpy().astype(np.uint8), "zn": zn.numpy()}.items():
+        flat = v.reshape(-1)
+        idx = sample_idx(flat.size)
+        out[k + "_sha256"] = np.array(sha(v)); out[k + "_idx"] = idx.astype(np.int64); out[k + "_val"] = flat[idx]
+        out[k + "_shape"] = np.array(v.shape, np.int64)
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     # tiny: edge cases + random, everything in full
@@ -260,6 +299,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "golden_rasterize.npz"), **rasterize_golden())
     np.savez_compressed(os.path.join(OUT, "golden_tiny_special.npz"), **special_values_golden())
     np.savez_compressed(os.path.join(OUT, "golden_tiny_bicubic.npz"), **bicubic_golden())
+    np.savez_compressed(os.path.join(OUT, "golden_demo.npz"), **demo_golden())
     raw = gravity_cases()
     azure, scannet = reference_gravity_rules()
     ga = [azure(r) for r in raw]; gs = [scannet(r) for r in raw]

@@ -179,3 +179,32 @@ def test_cuda_matches_reference_special_values(cuda_device):
                      (z, "z"), (zn, "zn")):
         assert C.count_bit_mismatches(got.cpu().numpy().reshape(g[key].shape), g[key]) == 0, key
     assert np.array_equal(mask.cpu().numpy().reshape(-1), g["mask"].reshape(-1))
+
+
+def test_cuda_demo_config_end_to_end(cuda_device):
+    """BASELINE config 1 (golden_demo.npz): raw IMU gravity of the eight demo frames -> vidc_condition_gravity, their klt track
+    files -> vidc_rasterize_sparse_depth, then the fused warp (bilinear and nearest depth) and unwarp at the main.py:243
+    intrinsics: every stage on the bits the reference's loader code and warper produced."""
+    from vi_depth_completion_b200.gravity import condition_gravity, rasterize_sparse_depth
+    from vi_depth_completion_b200.warping_2dof_alignment import Warping2DOFAlignment
+    g = np.load(os.path.join(GOLD, "golden_demo.npz"))
+    fx, fy, cx, cy = C.CAMERAS["S1"]
+    w = Warping2DOFAlignment(fx=fx, fy=fy, cx=cx, cy=cy)
+    Hh, Ww, B = int(w.H), int(w.W), 8
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    Ig, Ia = condition_gravity(t(g["raw_gravity"]), "azure")
+    assert C.count_bit_mismatches(Ig.cpu().numpy(), g["I_g"]) == 0 and C.count_bit_mismatches(Ia.cpu().numpy(), g["I_a"]) == 0
+    depth = rasterize_sparse_depth(t(g["tracks"]), g["counts"], g["fc"], g["cc"], Hh, Ww)
+    assert _sha(depth.cpu().numpy()) == str(g["depth_sha256"])
+    rgb = C.smooth_images(B, Hh, Ww, int(g["rgb_seed"]))
+    normals = C.random_images(B, Hh, Ww, int(g["normals_seed"]))[2]
+    H, rgb_w, depth_w, mask = w.warp_rgbd(t(rgb), depth, Ig, Ia)
+    _, _, depth_n, _ = w.warp_rgbd(t(rgb), depth, Ig, Ia, depth_mode="nearest")
+    _, zn = w.unwarp_normals(t(normals), Ig, Ia)
+    assert C.count_bit_mismatches(H.cpu().numpy(), g["Hm"]) == 0
+    assert _sha(rgb_w.cpu().numpy()) == str(g["y_rgb_sha256"])
+    assert _sha(depth_w.cpu().numpy().reshape(B, Hh, Ww)) == str(g["y_depth_sha256"])
+    assert _sha(depth_n.cpu().numpy().reshape(B, Hh, Ww)) == str(g["y_depth_nearest_sha256"])
+    assert _sha(mask.cpu().numpy().reshape(B, 1, Hh, Ww)) == str(g["mask_sha256"])
+    assert _sha(zn.cpu().numpy()) == str(g["zn_sha256"])
+    assert abs(float(mask.float().mean()) - float(g["valid_fraction"])) < 1e-6

@@ -143,3 +143,35 @@ def test_oracle_bicubic_matches_reference(oracle_mod):
         _, yd = o.warp_with_gravity_center_aligned(depth, I_g, I_a, interp_mode="bicubic")
     assert C.count_bit_mismatches(y, g["y_rgb"]) == 0
     assert C.count_bit_mismatches(yd, g["y_depth"].reshape(yd.shape)) == 0
+
+
+def test_oracle_demo_config(oracle_mod):
+    """BASELINE config 1 (golden_demo.npz): the eight demo frames' real gravity through the Demo loader's conditioning and the
+    warper at the main.py:243 intrinsics, the rasterised klt tracks as sparse depth -- SHA-256 of every output."""
+    g = _load("demo")
+    Ig, Ia = oracle_mod.condition_gravity(g["raw_gravity"], "azure")
+    assert C.count_bit_mismatches(Ig, g["I_g"]) == 0 and C.count_bit_mismatches(Ia, g["I_a"]) == 0
+    fx, fy, cx, cy = C.CAMERAS["S1"]
+    o = oracle_mod.Oracle(fx, fy, cx, cy)
+    B = 8
+    rgb = C.smooth_images(B, o.H, o.W, int(g["rgb_seed"]))
+    normals = C.random_images(B, o.H, o.W, int(g["normals_seed"]))[2]
+    # sparse depth rebuilt from the stored tracks (fp64 pixel arithmetic of dataset.py:496-510)
+    depth = np.zeros((B, o.H, o.W), np.float32)
+    for b in range(B):
+        for i in range(int(g["counts"][b])):
+            t = g["tracks"][b, i]
+            col, row = int(g["fc"][0] * (t[1] / t[3]) + g["cc"][0]), int(g["fc"][1] * (t[2] / t[3]) + g["cc"][1])
+            if 0 <= row < o.H and 0 <= col < o.W:
+                depth[b, row, col] = t[3]
+    assert _sha(depth.reshape(B, 1, o.H, o.W)) == str(g["depth_sha256"])
+    H, y = o.warp_with_gravity_center_aligned(rgb, Ig, Ia)
+    _, yd = o.warp_with_gravity_center_aligned(depth, Ig, Ia)
+    _, ydn = o.warp_with_gravity_center_aligned(depth, Ig, Ia, interp_mode="nearest")
+    _, z = o.inverse_warp_normal_image_with_gravity_center_aligned(normals, Ig, Ia)
+    assert C.count_bit_mismatches(H, g["Hm"]) == 0
+    assert _sha(y) == str(g["y_rgb_sha256"])
+    assert _sha(yd) == str(g["y_depth_sha256"])
+    assert _sha(ydn) == str(g["y_depth_nearest_sha256"])
+    assert _sha(oracle_mod.validity_mask(y).astype(np.uint8)) == str(g["mask_sha256"])
+    assert _sha(oracle_mod.normalize(z)) == str(g["zn_sha256"])
