@@ -211,6 +211,14 @@ int vidc_normalize3(const vidc_image *z, const vidc_image *out, void *stream);
 int vidc_normal_stats(const vidc_image *gt, const vidc_image *pred, const vidc_image *mask,
                       int32_t normalize_prediction, double *d_out, void *stream);
 
+/* Backward of the losses of normal_utils.py:7-34 w.r.t. pred_normals -- the reference back-propagates angle_L1 at
+   network_run.py:186,248.  loss_mode: 0 = compute_normal_vectors_loss_l1(normalize_prediction=True), 1 = the same with
+   normalize_prediction=False, 2 = compute_normal_vectors_loss_l2 (cosine).  d_stats = the four sums vidc_normal_stats
+   produced for the same tensors ([1] = sum(mask) is read), d_grad_loss = the upstream gradient of the scalar loss (one
+   float on the device, so nothing synchronises), grad_pred: (B,C,H,W) like pred, fully written (channels >= 3 get zeros). */
+int vidc_normal_loss_backward(const vidc_image *gt, const vidc_image *pred, const vidc_image *mask, int32_t loss_mode,
+                              const double *d_stats, const float *d_grad_loss, const vidc_image *grad_pred, void *stream);
+
 /* ---- host-buffer end-to-end entry point (bench.py `e2e`, simple embedders) ------------------
    One frame batch through the whole path with HOST buffers: H2D of rgb/depth/normals/gravity,
    warp_rgbd, unwarp_normals(normalize=1), D2H of the four outputs.  Buffers are contiguous NCHW.

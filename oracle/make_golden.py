@@ -167,6 +167,25 @@ def backward_golden():
     return out
 
 
+def loss_backward_golden():
+    """Row a10: the executed reference's normal_utils losses (normal_utils.py:7-34) and their autograd gradients w.r.t.
+    pred_normals -- the loss the reference back-propagates at network_run.py:186,248.  Inputs from seeds; pred has four
+    channels (only 0:3 are used, :8,:24), some pixels carry exact zeros (norm clamp) and the mask is a sparse 0/1 image."""
+    nu = load_normal_utils()
+    B, Hh, Ww = 3, 48, 64
+    pred, gt, maskf, up = C.loss_inputs(B, Hh, Ww, seed=17)
+    out = {"seed": np.int64(17)}
+    for name, fn in (("l1", lambda p, g, m: nu.compute_normal_vectors_loss_l1(g, p, m)),
+                     ("l1_raw", lambda p, g, m: nu.compute_normal_vectors_loss_l1(g, p, m, normalize_prediction=False)),
+                     ("l2", lambda p, g, m: nu.compute_normal_vectors_loss_l2(g, p, m))):
+        p = torch.from_numpy(pred).requires_grad_(True)
+        loss, angle = fn(p, torch.from_numpy(gt), torch.from_numpy(maskf))
+        (loss * float(up)).backward()
+        out[f"{name}_loss"] = loss.detach().numpy().copy(); out[f"{name}_angle"] = angle.detach().numpy().copy()
+        out[f"{name}_grad"] = p.grad.numpy().copy()
+    return out
+
+
 def rasterize_golden():
     """Row f2: the sparse-depth rasterisation block of the Demo loader (dataset.py:496-510), executed verbatim on synthetic
     tracks (with pixel collisions and out-of-range points) and on the eight demo_dataset track files."""
@@ -283,6 +302,10 @@ def demo_golden():
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--only-loss-backward" in sys.argv:
+        np.savez_compressed(os.path.join(OUT, "golden_tiny_loss_backward.npz"), **loss_backward_golden())
+        return
+    np.savez_compressed(os.path.join(OUT, "golden_tiny_loss_backward.npz"), **loss_backward_golden())
     # tiny: edge cases + random, everything in full
     eg, ea = C.edge_case_gravity()
     rg, ra = C.random_gravity(6, seed=4321, roll_deg=60, pitch_deg=45)

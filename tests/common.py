@@ -78,6 +78,18 @@ def random_images(B, H, W, seed, sparse_depth=False):
     return rgb, depth, normals
 
 
+def loss_inputs(B, H, W, seed):
+    """Inputs of the normal_utils losses: pred (B,4,H,W) ~ N(0,1) with a few exactly-zero vectors, unit-norm gt, a 0/1 mask
+    with ~60 % ones, and the upstream gradient of the scalar loss."""
+    rs = np.random.RandomState(seed)
+    pred = rs.randn(B, 4, H, W).astype(np.float32)
+    pred[0, :, 3::7, 2::5] = 0.0
+    gt = rs.randn(B, 3, H, W).astype(np.float32)
+    gt = (gt / np.sqrt((gt * gt).sum(1, keepdims=True))).astype(np.float32)
+    maskf = (rs.rand(B, 1, H, W) < 0.6).astype(np.float32)
+    return pred, gt, maskf, np.float32(1.7)
+
+
 SPECIAL_SCALES = np.array([0.0, 1e-42, 1e-35, 1e-31, 1e-25, 1e-19, 1e-15, 1e-9, 1.0, 1e9, 1e15, 1e19, 1e25, 1e35, np.inf],
                           dtype=np.float32)
 

@@ -346,4 +346,60 @@ normal_stats_kernel(ImgView gt, ImgView pred, ImgView mask, int normalize_predic
     }
 }
 
+// Backward of the two losses of normal_utils.py w.r.t. pred_normals (the training loss of network_run.py:186,248), one pass.
+//   mode 0: compute_normal_vectors_loss_l1, normalize_prediction=True   loss = sum|n^ m - g m| / sum(m)      (:20-34)
+//   mode 1: the same with normalize_prediction=False                     (n^ = pred)
+//   mode 2: compute_normal_vectors_loss_l2                               loss = -sum(cos_sim(pred, g)) / sum(m) (:7-10, NOT masked)
+// stats[1] = sum(mask) from the forward pass (vidc_normal_stats); *grad_loss = upstream gradient of the scalar loss.
+// Chain rules are torch's: L1Loss(sum) -> sign(a - b) with sign(0) = 0; F.normalize -> x / norm.clamp_min(1e-12), the clamp
+// passing gradient only where norm >= 1e-12; cosine_similarity clamps each norm at 1e-8.  Channels >= 3 of pred get zeros.
+__global__ void __launch_bounds__(256)
+normal_loss_backward_kernel(ImgView gt, ImgView pred, ImgView mask, int mode, const double* __restrict__ stats,
+                            const float* __restrict__ grad_loss, ImgViewOut gp) {
+    const int b = blockIdx.z;
+    const int X = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (X >= gt.w || Y >= gt.h) return;
+    const float go = __ldg(grad_loss) / (float)__ldg(stats + 1);
+    const float* __restrict__ pp = pred.p + (long long)b * pred.sn + Y * pred.sh + X * pred.sw;
+    const float* __restrict__ pg = gt.p + (long long)b * gt.sn + Y * gt.sh + X * gt.sw;
+    float* __restrict__ po = gp.p + (long long)b * gp.sn + Y * gp.sh + X * gp.sw;
+    const float m = __ldg(mask.p + (long long)b * mask.sn + Y * mask.sh + X * mask.sw);
+    const float r[3] = {__ldg(pp), __ldg(pp + pred.sc), __ldg(pp + 2 * pred.sc)};
+    const float g[3] = {__ldg(pg), __ldg(pg + gt.sc), __ldg(pg + 2 * gt.sc)};
+    const float nr = sqrtf((r[0] * r[0] + r[1] * r[1]) + r[2] * r[2]);
+    float d[3];
+    if (mode == 2) {
+        const float ng = fmaxf(sqrtf((g[0] * g[0] + g[1] * g[1]) + g[2] * g[2]), 1e-8f);
+        const float nrc = fmaxf(nr, 1e-8f);
+        const float dot = (r[0] * g[0] + r[1] * g[1]) + r[2] * g[2];
+        const float k = nr >= 1e-8f ? dot / (nrc * nrc * nrc * ng) : 0.0f;     // d(1/|r|)/dr term, absent while the norm is clamped
+#pragma unroll
+        for (int c = 0; c < 3; ++c) d[c] = -go * (g[c] / (nrc * ng) - k * r[c]);
+    } else {
+        float n[3] = {r[0], r[1], r[2]};
+        const float nn = clamp_min_eps(nr);
+        if (mode == 0) { n[0] = r[0] / nn; n[1] = r[1] / nn; n[2] = r[2] / nn; }
+        float dn[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float diff = n[c] * m - g[c] * m;
+            const float sg = diff > 0.0f ? 1.0f : (diff < 0.0f ? -1.0f : 0.0f);  // torch.sign: 0 for 0 and for NaN
+            dn[c] = go * sg * m;
+        }
+        if (mode == 0) {
+            const float dd = (dn[0] * r[0] + dn[1] * r[1]) + dn[2] * r[2];
+            const float k = nr >= 1e-12f ? dd / (nn * nn * nr) : 0.0f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) d[c] = dn[c] / nn - k * r[c];
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) d[c] = dn[c];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) po[c * gp.sc] = d[c];
+    for (int c = 3; c < gp.c; ++c) po[c * gp.sc] = 0.0f;
+}
+
 }  // namespace vidc_k

@@ -3,7 +3,8 @@ networks/surface_normal.py (:150-156, :170), on the same C-ABI kernels.
 
 Same function names and argument meaning as the reference; each loss function is ONE fused pass over HBM
 (the reference makes ~8 element-wise passes and two reductions) and does not synchronise with the host
-(the reference calls .item() at normal_utils.py:32).  `Normalize` is undefined in the reference
+(the reference calls .item() at normal_utils.py:32), and is differentiable w.r.t. pred_normals through one fused backward
+pass (the reference back-propagates this loss, network_run.py:186,248).  `Normalize` is undefined in the reference
 (normal_utils.py:12,24); the evident intent, F.normalize(x, dim=1), is what the kernels implement.
 """
 import ctypes
@@ -32,14 +33,19 @@ def Normalize(x):
     return out
 
 
-def _stats(norm_gt, pred_normals, mask, normalize_prediction):
-    _require_cuda_f32(norm_gt, "norm_gt")
-    _require_cuda_f32(pred_normals, "pred_normals")
-    if not mask.is_cuda:
+def _mask4(mask):
+    if not isinstance(mask, torch.Tensor) or not mask.is_cuda:
         raise RuntimeError("mask: expected a CUDA tensor")
     mask = mask.float()                                           # normal_utils.py:21
     if mask.dim() == 3:
         mask = mask.view(mask.shape[0], 1, mask.shape[1], mask.shape[2])
+    return mask
+
+
+def _stats(norm_gt, pred_normals, mask, normalize_prediction):
+    _require_cuda_f32(norm_gt, "norm_gt")
+    _require_cuda_f32(pred_normals, "pred_normals")
+    mask = _mask4(mask)
     dev = norm_gt.device
     out = torch.empty(4, dtype=torch.float64, device=dev)
     gi, pi, mi = _image(norm_gt), _image(pred_normals), _image(mask)
@@ -49,20 +55,53 @@ def _stats(norm_gt, pred_normals, mask, normalize_prediction):
     return out        # [sum(angle*mask), sum(mask), sum|n*mask - gt*mask|, sum(cosine_similarity)]
 
 
+_L1_NORMALIZED, _L1_RAW, _L2_COSINE = 0, 1, 2
+
+
+class _NormalLossFn(torch.autograd.Function):
+    """(loss, angle) of normal_utils.py:7-34 with the gradient of the loss w.r.t. pred_normals -- the reference
+    back-propagates it (network_run.py:186 -> total_loss.backward() at :248).  Forward: one fused pass
+    (vidc_normal_stats); backward: one fused pass (vidc_normal_loss_backward), no host synchronisation in either.
+    `angle` is the logged metric (network_run.py:189, `.item()`): it is marked non-differentiable here, while in the
+    reference it happens to carry a graph nobody uses.  norm_gt and mask are data and get no gradient."""
+
+    @staticmethod
+    def forward(ctx, pred_normals, norm_gt, mask, loss_mode):
+        s = _stats(norm_gt, pred_normals, mask, loss_mode != _L1_RAW)
+        loss = ((-s[3] if loss_mode == _L2_COSINE else s[2]) / s[1]).float()
+        angle = s[0].float()
+        ctx.loss_mode = loss_mode
+        ctx.save_for_backward(pred_normals, norm_gt, _mask4(mask), s)
+        ctx.mark_non_differentiable(angle)
+        return loss, angle
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_angle):
+        pred, gt, mask, s = ctx.saved_tensors
+        dev = pred.device
+        gp = torch.empty_like(pred)
+        go = grad_loss.to(device=dev, dtype=torch.float32).contiguous()
+        gi, pi, mi, oi = _image(gt), _image(pred), _image(mask), _image(gp)
+        with torch.cuda.device(dev):
+            check(lib().vidc_normal_loss_backward(ctypes.byref(gi), ctypes.byref(pi), ctypes.byref(mi), ctx.loss_mode,
+                                                  s.data_ptr(), go.data_ptr(), ctypes.byref(oi), _stream_ptr(dev)))
+        return gp, None, None, None
+
+
+def _loss(norm_gt, pred_normals, mask, loss_mode):
+    if isinstance(pred_normals, torch.Tensor) and pred_normals.dim() != 4:
+        raise RuntimeError("pred_normals: expected (B,>=3,H,W)")
+    return _NormalLossFn.apply(pred_normals, norm_gt, mask, loss_mode)
+
+
 # normal_utils.py:7-17
 def compute_normal_vectors_loss_l2(norm_gt, pred_normals, mask):
-    s = _stats(norm_gt, pred_normals, mask, True)
-    loss = (-s[3] / s[1]).float()
-    angle = s[0].float()
-    return loss, angle
+    return _loss(norm_gt, pred_normals, mask, _L2_COSINE)
 
 
 # normal_utils.py:20-34
 def compute_normal_vectors_loss_l1(norm_gt, pred_normals, mask, normalize_prediction=True):
-    s = _stats(norm_gt, pred_normals, mask, normalize_prediction)
-    loss = (s[2] / s[1]).float()
-    angle = s[0].float()
-    return loss, angle
+    return _loss(norm_gt, pred_normals, mask, _L1_NORMALIZED if normalize_prediction else _L1_RAW)
 
 
 # networks/surface_normal.py:151-152

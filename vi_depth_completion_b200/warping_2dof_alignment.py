@@ -51,9 +51,16 @@ def _gravity(I_g: torch.Tensor, I_a: torch.Tensor, device):
     _require_cuda_f32(I_a, "I_a")
     if I_g.device != device or I_a.device != device:
         raise RuntimeError(f"I_g / I_a must live on {device}, got {I_g.device} / {I_a.device}")
-    B = I_g.shape[0]
-    # the reference does I_g.view(B,3,1), I_a.view(B,1,3)  (:38-39)
-    return I_g.reshape(B, 3).contiguous(), I_a.reshape(I_a.shape[0], 3).contiguous()
+    B, Ba = I_g.shape[0], I_a.shape[0]
+    if I_g.numel() != 3 * B or I_a.numel() != 3 * Ba:            # .view(B,3,1) / .view(B,1,3) at :38-39
+        raise RuntimeError(f"I_g / I_a: expected 3 components per frame, got shapes {tuple(I_g.shape)} / {tuple(I_a.shape)}")
+    # the kernels read 3*B floats from both: a shorter I_a must never reach them.  The reference fails in the same two
+    # places: I_a[i] in the loop of :40-41 (IndexError) or the batched product I_a @ I_g at :43 (RuntimeError).
+    if Ba < B:
+        raise IndexError(f"index {Ba} is out of bounds for dimension 0 with size {Ba} (I_a has {Ba} frames, I_g has {B})")
+    if Ba > B:
+        raise RuntimeError(f"I_a has {Ba} frames but I_g has {B}: batch dimensions of I_a @ I_g must match (ref :43)")
+    return I_g.reshape(B, 3).contiguous(), I_a.reshape(Ba, 3).contiguous()
 
 
 class _WarpFn(torch.autograd.Function):
