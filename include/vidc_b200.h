@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define VIDC_ABI_VERSION 1
+#define VIDC_ABI_VERSION 2
 
 typedef enum vidc_status {
     VIDC_OK = 0,
@@ -101,6 +101,12 @@ const char *vidc_last_error(void);
 /* Replaces Warping2DOFAlignment.__init__ (:6-24).  Host only. */
 int vidc_camera_init(double fx, double fy, double cx, double cy, vidc_camera *cam);
 
+/* Bytes of device scratch every `d_params_ws` argument below must provide for a batch of B frames: the B vidc_frame_params
+   blocks followed by the per-tile tables of the kernels (today: the footprint boxes of the inverse warp, 16 bytes per 32x32
+   tile).  16-byte aligned, caller-owned, may be reused across calls on the same stream.  Host only; 0 for B <= 0.
+   (The reference re-allocates its scratch in every call, :118-122; there is no counterpart.) */
+size_t vidc_workspace_bytes(const vidc_camera *cam, int32_t B);
+
 /* Dataset-side gravity conditioning on device: raw IMU gravity (B,3) -> I_g, I_a.
    rule 0 = Azure / Demo loaders (dataset.py:334-345, :472-483: negate y and z; psi < 1e-4 or cos(pitch) > 0.707
             -> a = [0,1,0], else a = [0, cos(pitch), sin(pitch)]);
@@ -127,7 +133,7 @@ int vidc_build_homography(const vidc_camera *cam, const float *d_Ig, const float
 
 /* Replaces warp_with_gravity_center_aligned (:108-156): fused params + grid + grid_sample.
    x: (B,C,Hin,Win) any strides; y: (B,C,cam.H,cam.W).  d_H_out (B,3,3) may be NULL.
-   d_params_ws: caller-owned scratch of B vidc_frame_params (may alias across calls). */
+   d_params_ws: caller-owned scratch of vidc_workspace_bytes(cam, B) bytes (B vidc_frame_params first; may alias across calls). */
 int vidc_warp_forward(const vidc_camera *cam, const vidc_image *x, const float *d_Ig, const float *d_Ia,
                       int32_t B_gravity, vidc_interp mode, vidc_frame_params *d_params_ws,
                       float *d_H_out, const vidc_image *y, void *stream);

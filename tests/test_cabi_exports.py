@@ -23,7 +23,7 @@ def test_header_symbols_are_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), f"{n} is declared in include/vidc_b200.h but not exported"
     assert set(names) == set(_cabi.EXPORTED_SYMBOLS), "ctypes binding and header disagree"
-    assert lib.vidc_abi_version() == 1
+    assert lib.vidc_abi_version() == 2
 
 
 def test_struct_layouts_match_header():

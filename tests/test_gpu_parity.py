@@ -260,8 +260,8 @@ print("VARIANT_OK")
 
 
 @pytest.mark.parametrize("env", [{"VIDC_SHEAR": "0"}, {"VIDC_SHEAR": "1"}, {"VIDC_SHEAR": "2"}, {"VIDC_TMA": "1"},
-                                 {"VIDC_TILE_SKIP": "0"}],
-                         ids=["straight-rows", "sheared-forward", "sheared-both", "tma-staged", "no-tile-skip"])
+                                 {"VIDC_TILE_SKIP": "0"}, {"VIDC_INV_BOX": "1"}],
+                         ids=["straight-rows", "sheared-forward", "sheared-both", "tma-staged", "no-tile-skip", "inverse-box-staged"])
 def test_kernel_variants_match_oracle(cuda_device, oracle_mod, env):
     """Every kernel family behind the fused entry points, each selected by its environment switch in a fresh process:
     straight row segments (VIDC_SHEAR=0), sheared forward rows only (=1), sheared forward + inverse (=2, the default) and

@@ -46,6 +46,7 @@ _SIGNATURES = {
     "vidc_abi_version": (ctypes.c_int, []),
     "vidc_last_error": (ctypes.c_char_p, []),
     "vidc_launch_count": (ctypes.c_uint64, []),
+    "vidc_workspace_bytes": (ctypes.c_size_t, [_P(VidcCamera), ctypes.c_int32]),
     "vidc_camera_init": (ctypes.c_int, [ctypes.c_double] * 4 + [_P(VidcCamera)]),
     "vidc_frame_params_compute": (ctypes.c_int, [_P(VidcCamera), c_f32p, c_f32p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
     "vidc_build_homography": (ctypes.c_int, [_P(VidcCamera), c_f32p, c_f32p, ctypes.c_int32, c_f32p, c_f32p, c_f32p, ctypes.c_void_p]),
@@ -101,8 +102,8 @@ def lib():
             fn = getattr(l, name)  # AttributeError if the library does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if l.vidc_abi_version() != 1:
-            raise RuntimeError(f"libvidc_b200.so ABI version {l.vidc_abi_version()} != 1; rebuild it")
+        if l.vidc_abi_version() != 2:
+            raise RuntimeError(f"libvidc_b200.so ABI version {l.vidc_abi_version()} != 2; rebuild it")
         _lib = l
     return _lib
 

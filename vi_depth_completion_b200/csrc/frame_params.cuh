@@ -127,5 +127,117 @@ VIDC_HD bool tile_certainly_exterior(const vidc_frame_params& p, const vidc_came
     return ok && (ix_hi < -1.0f - mx || ix_lo > Wf + mx || iy_hi < -1.0f - my || iy_lo > Hf + my);
 }
 
+// ---- inverse warp: per-tile footprint boxes (kernels_box.cuh) -----------------------------------------------------------------
+// The inverse warp of a 32x32 camera tile reads a canvas patch of about the same size.  unwarp_normals_box_kernel stages
+// that patch in shared memory with coalesced 128-bit loads and takes its bilinear taps from there; which patch to stage is
+// decided here, once per frame and tile, by the per-frame kernel.  NOT part of any result: a pixel whose taps do not lie
+// inside the staged box takes the kernel's direct (global-memory) path, so a wrong box can only cost time.
+//
+// Entry layout (4 x uint32 per tile):
+//   [0] box A: (x0 & 0xffff) | (y0 << 16)          [1] w | h << 8 | nsub << 16 | sigma << 20 | div_proven << 21
+//   [2] box B: (x0 & 0xffff) | (y0 << 16)          [3] w | h << 8
+// nsub = 1: box A covers the whole tile; 2: A covers tile rows 0..15 and B rows 16..31; 0: nothing is staged (pole inside the
+// tile or a footprint that does not fit).  x0 is a multiple of 4 (it may be -4), the box includes the +1 taps and may overhang
+// the image by up to 4 columns / 1 row (staged as zeros = padding_mode='zeros').  sigma selects the row pitch of the staging
+// buffer (65 or 63 floats, i.e. +-1 modulo the 32 banks) so that the 32 taps of a canvas row segment fall into distinct banks.
+#ifndef VIDC_BOX_MAX_H
+#define VIDC_BOX_MAX_H 40
+#endif
+constexpr int kBoxMaxW = 60, kBoxMaxH = VIDC_BOX_MAX_H;        // 60: whole float4 groups (columns 56..59) stay inside a 63-float row pitch
+
+struct InvBox { int x0, y0, w, h; bool ok; };
+
+VIDC_HD void inv_pixel_coords(const vidc_frame_params& p, const vidc_camera& cam, float X, float Y, float& ix, float& iy, float& s_out,
+                              float& s_terms) {
+    const float* Hm = p.H;
+    const float u = fmaf(Hm[1], Y, Hm[0] * X) + Hm[2];
+    const float v = fmaf(Hm[4], Y, Hm[3] * X) + Hm[5];
+    const float s = fmaf(Hm[7], Y, Hm[6] * X) + Hm[8];
+    const float tx = u / s, ty = v / s;
+    const float gx = cam.inv_half_w * (p.kw * (tx - p.px_min) - cam.cx);
+    const float gy = cam.inv_half_h * (p.kh * (ty - p.py_min) - cam.cy);
+    ix = fmaf(gx + 1.0f, (float)cam.W, -1.0f) * 0.5f;
+    iy = fmaf(gy + 1.0f, (float)cam.H, -1.0f) * 0.5f;
+    s_out = s;
+    s_terms = fabsf(Hm[6] * X) + fabsf(Hm[7] * Y) + fabsf(Hm[8]);
+}
+
+// Bounding box of the taps of camera pixels [X0, X1] x [Y0, Y1] (inclusive).  Over a rectangle on which the projective
+// denominator keeps its sign the map is continuous and takes the rectangle into the convex quadrilateral of its mapped
+// corners, so the extremes of both coordinates are at the corners; 0.02 px absorbs the fp32 evaluation error.
+VIDC_HD InvBox inv_rect_box(const vidc_frame_params& p, const vidc_camera& cam, int X0, int Y0, int X1, int Y1) {
+    InvBox b; b.x0 = 0; b.y0 = 0; b.w = 1; b.h = 1; b.ok = false;
+    float xlo = 3.0e38f, xhi = -3.0e38f, ylo = 3.0e38f, yhi = -3.0e38f, slo = 3.0e38f, shi = -3.0e38f;
+    bool ok = true;
+    for (int c = 0; c < 4; ++c) {
+        float ix, iy, s, st;
+        inv_pixel_coords(p, cam, (float)((c & 1) ? X1 : X0), (float)((c >> 1) ? Y1 : Y0), ix, iy, s, st);
+        ok = ok && fabsf(s) > 1e-3f * st && fabsf(ix) < 1e8f && fabsf(iy) < 1e8f;       // also rejects NaN
+        xlo = fminf(xlo, ix); xhi = fmaxf(xhi, ix); ylo = fminf(ylo, iy); yhi = fmaxf(yhi, iy);
+        slo = fminf(slo, s); shi = fmaxf(shi, s);
+    }
+    ok = ok && (slo > 0.0f || shi < 0.0f);
+    if (!ok) return b;
+    int x_lo = (int)floorf(xlo - 0.02f), x_hi = (int)floorf(xhi + 0.02f) + 1;
+    int y_lo = (int)floorf(ylo - 0.02f), y_hi = (int)floorf(yhi + 0.02f) + 1;
+    x_lo = x_lo < -1 ? -1 : x_lo; y_lo = y_lo < -1 ? -1 : y_lo;
+    x_hi = x_hi > cam.W ? cam.W : x_hi; y_hi = y_hi > cam.H ? cam.H : y_hi;
+    if (x_hi <= x_lo || y_hi <= y_lo) { b.ok = true; return b; }          // maps outside the canvas: empty box, all zeros
+    b.x0 = (x_lo >> 2) << 2;                                              // floor to a multiple of 4 (arithmetic shift)
+    b.y0 = y_lo;
+    b.w = x_hi - b.x0 + 1;
+    b.h = y_hi - y_lo + 1;
+    b.ok = b.w <= kBoxMaxW && b.h <= kBoxMaxH;
+    if (!b.ok) { b.x0 = 0; b.y0 = 0; b.w = 1; b.h = 1; }
+    return b;
+}
+
+// The shared-reciprocal division of the hot kernels (kernels_fast.cuh: div2_rn) is the correctly rounded quotient while
+// |s| lies in [2^-40, 2^40] and each numerator is zero or lies in [2^-80, 2^80].  For the inverse warp u, v, s are
+// fma(H1, Y, H0 X) + H2 with integer pixel coordinates 0 <= X, Y < 2^15, so a non-zero numerator is a multiple of the
+// smallest ulp among its non-zero coefficients: with every non-zero |H_k| in [2^-56, 2^60] it is >= 2^-80 and <= 2^80.
+// s is affine in (X, Y): if its four image-corner values share a sign and exceed 2^-10 of M = |H6| W + |H7| H + |H8| (the
+// rounding error of the evaluation is < 2^-21 M), then 2^-11 M <= |s| <= 1.01 M everywhere; M in [2^-25, 2^39] closes it.
+// A frame that passes runs the inverse kernel WITHOUT the per-pixel window test (six instructions per pixel).
+VIDC_HD bool inv_division_proven(const vidc_frame_params& p, const vidc_camera& cam) {
+    const float* Hm = p.H;
+    bool ok = cam.W <= 32768 && cam.H <= 32768;
+    for (int k = 0; k < 9; ++k) {
+        const float a = fabsf(Hm[k]);
+        ok = ok && (a == 0.0f || (a >= 0x1p-56f && a <= 0x1p60f));        // NaN fails both
+    }
+    const float Wm = (float)(cam.W - 1), Hh = (float)(cam.H - 1);
+    const float M = fabsf(Hm[6]) * (float)cam.W + fabsf(Hm[7]) * (float)cam.H + fabsf(Hm[8]);
+    ok = ok && M >= 0x1p-25f && M <= 0x1p39f;
+    float slo = 3.0e38f, shi = -3.0e38f;
+    for (int c = 0; c < 4; ++c) {
+        const float s = fmaf(Hm[7], (c >> 1) ? Hh : 0.0f, Hm[6] * ((c & 1) ? Wm : 0.0f)) + Hm[8];
+        slo = fminf(slo, s); shi = fmaxf(shi, s);
+    }
+    const float m = slo > 0.0f ? slo : -shi;                              // smallest corner magnitude if the sign is common
+    return ok && (slo > 0.0f || shi < 0.0f) && m >= 0x1p-10f * M;
+}
+
+VIDC_HD void inv_tile_boxes(const vidc_frame_params& p, const vidc_camera& cam, int tx, int ty, bool div_proven, uint32_t out[4]) {
+    const int X0 = tx * 32, Y0 = ty * 32;
+    const int X1 = (X0 + 31 < cam.W - 1) ? X0 + 31 : cam.W - 1, Y1 = (Y0 + 31 < cam.H - 1) ? Y0 + 31 : cam.H - 1;
+    // sigma: sign of d(canvas x)/dX * d(canvas y)/dX at the tile centre (kw, kh > 0 and the common 1/s^2 drop out)
+    float ix, iy, s, st;
+    const float Xc = (float)(X0 + 16), Yc = (float)(Y0 + 16);
+    inv_pixel_coords(p, cam, Xc, Yc, ix, iy, s, st);
+    const float u = fmaf(p.H[1], Yc, p.H[0] * Xc) + p.H[2], v = fmaf(p.H[4], Yc, p.H[3] * Xc) + p.H[5];
+    const float dxdX = p.H[0] * s - u * p.H[6], dydX = p.H[3] * s - v * p.H[6];
+    const uint32_t sigma = (dxdX * dydX >= 0.0f) ? 1u : 0u;
+    InvBox a = inv_rect_box(p, cam, X0, Y0, X1, Y1), b2; b2.x0 = 0; b2.y0 = 0; b2.w = 1; b2.h = 1; b2.ok = false;
+    uint32_t nsub = a.ok ? 1u : 0u;
+    if (!a.ok && Y0 + 16 <= Y1) {
+        const InvBox h0 = inv_rect_box(p, cam, X0, Y0, X1, Y0 + 15), h1 = inv_rect_box(p, cam, X0, Y0 + 16, X1, Y1);
+        if (h0.ok && h1.ok) { a = h0; b2 = h1; nsub = 2u; }
+    }
+    out[0] = ((uint32_t)a.x0 & 0xffffu) | ((uint32_t)a.y0 << 16);
+    out[1] = (uint32_t)a.w | ((uint32_t)a.h << 8) | (nsub << 16) | (sigma << 20) | ((div_proven ? 1u : 0u) << 21);
+    out[2] = ((uint32_t)b2.x0 & 0xffffu) | ((uint32_t)b2.y0 << 16);
+    out[3] = (uint32_t)b2.w | ((uint32_t)b2.h << 8);
+}
 
 }  // namespace vidc

@@ -142,6 +142,7 @@ class Warping2DOFAlignment:
         self.H = np.int64(self._cam.H)
         self.device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
         self._const_cache = {}
+        self._ws_bytes = {}
 
     # ---- constant tensors the reference exposes as attributes (:15-24), built lazily ----------
     def _const(self, name):
@@ -172,9 +173,12 @@ class Warping2DOFAlignment:
     I3 = property(lambda self: self._const("I3"))
 
     def _params_ws(self, B, device):
-        """Scratch for B vidc_frame_params (192 B each).  Allocated per call from torch's stream-ordered caching allocator
+        """Scratch of vidc_workspace_bytes(cam, B): B vidc_frame_params (192 B each) + the kernels' per-tile tables.  Allocated per call from torch's stream-ordered caching allocator
         (a microsecond), so concurrent use of one instance from several streams never shares scratch."""
-        return torch.empty((max(B, 1), _cabi.FRAME_PARAMS_FLOATS), dtype=torch.float32, device=device)
+        nbytes = self._ws_bytes.get(B)
+        if nbytes is None:
+            nbytes = self._ws_bytes[B] = max(int(lib().vidc_workspace_bytes(ctypes.byref(self._cam), B)), 4 * _cabi.FRAME_PARAMS_FLOATS)
+        return torch.empty((nbytes // 4,), dtype=torch.float32, device=device)
 
     def _skewsymm(self, x):  # :26-32, kept for API compatibility (pure tensor ops, no host sync)
         x = x.reshape(-1)
