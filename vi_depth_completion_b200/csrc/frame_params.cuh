@@ -127,6 +127,37 @@ VIDC_HD bool tile_certainly_exterior(const vidc_frame_params& p, const vidc_came
     return ok && (ix_hi < -1.0f - mx || ix_lo > Wf + mx || iy_hi < -1.0f - my || iy_lo > Hf + my);
 }
 
+// Source-image bounding box of forward canvas tile (tx, ty) -- the rows an L2 prefetch one wave ahead should ask for
+// (kernels_shear.cuh).  A hint only, from the same four mapped corners as the exterior test: out = {x0, y0, w, h} in source
+// pixels, w = 0 when there is nothing to prefetch (exterior, ill-conditioned or non-finite tile).
+VIDC_HD void fwd_tile_src_box(const vidc_frame_params& p, const vidc_camera& cam, int tx, int ty, uint32_t out[4]) {
+    out[0] = out[1] = out[2] = out[3] = 0u;
+    const float Wf = (float)cam.W, Hf = (float)cam.H;
+    const float X[2] = {(float)(tx * 32), fminf((float)(tx * 32 + 31), Wf - 1.0f)};
+    const float Y[2] = {(float)(ty * 32), fminf((float)(ty * 32 + 31), Hf - 1.0f)};
+    float ix_lo = 3.0e38f, ix_hi = -3.0e38f, iy_lo = 3.0e38f, iy_hi = -3.0e38f, s_lo = 3.0e38f, s_hi = -3.0e38f;
+    bool ok = true;
+    for (int c = 0; c < 4; ++c) {
+        const float px = p.ikw * X[c & 1] + p.px_min, py = p.ikh * Y[c >> 1] + p.py_min;
+        const float t0 = p.Hinv[6] * px, t1 = p.Hinv[7] * py;
+        const float s = t0 + t1 + p.Hinv[8];
+        const float u = p.Hinv[0] * px + p.Hinv[1] * py + p.Hinv[2];
+        const float v = p.Hinv[3] * px + p.Hinv[4] * py + p.Hinv[5];
+        ok = ok && fabsf(s) > 1e-3f * (fabsf(t0) + fabsf(t1) + fabsf(p.Hinv[8]));
+        const float ix = ((u / s - cam.cx) * cam.inv_half_w + 1.0f) * Wf * 0.5f - 0.5f;
+        const float iy = ((v / s - cam.cy) * cam.inv_half_h + 1.0f) * Hf * 0.5f - 0.5f;
+        ok = ok && fabsf(ix) < 1e8f && fabsf(iy) < 1e8f;
+        ix_lo = fminf(ix_lo, ix); ix_hi = fmaxf(ix_hi, ix); iy_lo = fminf(iy_lo, iy); iy_hi = fmaxf(iy_hi, iy);
+        s_lo = fminf(s_lo, s); s_hi = fmaxf(s_hi, s);
+    }
+    if (!(ok && (s_lo > 0.0f || s_hi < 0.0f))) return;
+    int x0 = (int)floorf(ix_lo), x1 = (int)floorf(ix_hi) + 1, y0 = (int)floorf(iy_lo), y1 = (int)floorf(iy_hi) + 1;
+    x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0;
+    x1 = x1 > cam.W - 1 ? cam.W - 1 : x1; y1 = y1 > cam.H - 1 ? cam.H - 1 : y1;
+    if (x1 < x0 || y1 < y0) return;
+    out[0] = (uint32_t)x0; out[1] = (uint32_t)y0; out[2] = (uint32_t)(x1 - x0 + 1); out[3] = (uint32_t)(y1 - y0 + 1);
+}
+
 // ---- inverse warp: per-tile footprint boxes (kernels_box.cuh) -----------------------------------------------------------------
 // The inverse warp of a 32x32 camera tile reads a canvas patch of about the same size.  unwarp_normals_box_kernel stages
 // that patch in shared memory with coalesced 128-bit loads and takes its bilinear taps from there; which patch to stage is

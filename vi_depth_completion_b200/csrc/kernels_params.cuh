@@ -44,7 +44,8 @@ __global__ void frame_params_kernel(vidc_camera cam, const float* __restrict__ I
 // The test itself is vidc::tile_certainly_exterior (frame_params.cuh, host / device: tests/ run it on the CPU).
 __global__ void __launch_bounds__(320) frame_params_tiles_kernel(vidc_camera cam, const float* __restrict__ Ig,
                                                                  const float* __restrict__ Ia, int B,
-                                                                 vidc_frame_params* __restrict__ out, float* __restrict__ H_out) {
+                                                                 vidc_frame_params* __restrict__ out, float* __restrict__ H_out,
+                                                                 uint4* __restrict__ src_boxes) {
     __shared__ vidc_frame_params sp;
     const int i = blockIdx.x, t = threadIdx.x;
     if (t == 0) {
@@ -68,6 +69,13 @@ __global__ void __launch_bounds__(320) frame_params_tiles_kernel(vidc_camera cam
     if ((t & 31) == 0) o[37 + (t >> 5)] = __uint_as_float(bal);      // reserved[0..9]: 320 tile bits
     if (t == 1) o[47] = 0.0f;                                        // reserved[10]
     if (H_out && t < 9) H_out[9 * i + t] = sp.H[t];
+    if (src_boxes) {                                                 // prefetch hints of the sheared forward kernels
+        for (int k = t; k < nt; k += blockDim.x) {
+            uint32_t e[4];
+            vidc::fwd_tile_src_box(sp, cam, k % tiles_x, k / tiles_x, e);
+            src_boxes[(size_t)i * nt + k] = make_uint4(e[0], e[1], e[2], e[3]);
+        }
+    }
 }
 
 // dataset.py gravity conditioning on device: raw IMU gravity -> (I_g, I_a)

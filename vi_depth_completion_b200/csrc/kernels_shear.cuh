@@ -75,6 +75,30 @@ __device__ __forceinline__ bool tile_marked_exterior(const vidc_frame_params* __
     return (word >> (tile & 31u)) & 1u;
 }
 
+// L2 prefetch for the CTA that will run about half a wave later: the forward warp is bound by the latency of L1 misses that go
+// all the way to DRAM (L2 hit rate 24 %, long-scoreboard 17.5 per issue: profiles/r1_shear_final_ncu_summary.txt); asking L2 for
+// the rows of that tile's source box now turns them into L2 hits.  The box comes from the per-frame kernel
+// (vidc::fwd_tile_src_box); thread -> (row, 128-byte segment); a hint only, no result depends on it.
+template <bool HAS_D>
+__device__ __forceinline__ void prefetch_source_box_l2(const FwdArgs& a, int W, int H) {
+    if (!a.src_boxes) return;
+    int px = (int)blockIdx.x + a.pf_x, py = (int)blockIdx.y + a.pf_y, pz = (int)blockIdx.z + a.pf_z;
+    if (px >= (int)gridDim.x) { px -= gridDim.x; ++py; }
+    if (py >= (int)gridDim.y) { py -= gridDim.y; ++pz; }
+    if (pz >= (int)gridDim.z) return;
+    const uint4 e = __ldg(a.src_boxes + (((size_t)pz * gridDim.y + py) * gridDim.x + px));
+    if (e.z == 0u) return;
+    const int tid = threadIdx.y * 32 + threadIdx.x, seg = tid & 3, r = tid >> 2;           // <= 64 rows x 4 segments of 32 px
+    if (r >= (int)e.w || seg * 32 >= (int)e.z + (int)(e.x & 31u)) return;
+    const long long off = (long long)(e.y + r) * W + ((e.x & ~31u) + seg * 32);
+    if ((int)((e.x & ~31u) + seg * 32) >= W) return;
+    const float* __restrict__ rgb = a.rgb + (long long)pz * a.rgb_sn + off;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(rgb));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(rgb + W * H));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(rgb + 2 * W * H));
+    if (HAS_D) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dep + (long long)pz * a.dep_sn + off));
+}
+
 // ---- forward: RGB (3 planes) + optional depth, mask, coverage -------------------------------------------------------
 template <int GW, int GH, bool HAS_D, bool ALONG_Y>
 __device__ __forceinline__ void warp_rgbd_shear_segments(const FwdArgs& a, const float* pr, float4 (*tile)[32], int sh_l) {
@@ -165,6 +189,7 @@ warp_rgbd_shear_kernel(const __grid_constant__ FwdArgs a) {
     __shared__ __align__(16) float4 tile[32][32];
     const int b = blockIdx.z, lane = threadIdx.x, warp = threadIdx.y;
     const int tileX0 = blockIdx.x * TILE_W, tileY0 = blockIdx.y * TILE_H;
+    prefetch_source_box_l2<HAS_D>(a, W, H);
     if (tile_marked_exterior(a.prm + b)) {                         // CTA-uniform: nothing of the source lands here, all zeros
         const int tid = warp * 32 + lane, row = tid >> 3, c4 = (tid & 7) * 4;
         const int Yo = tileY0 + row, Xo = tileX0 + c4;
