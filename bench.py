@@ -5,7 +5,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one batch of synthetic frames held by this rank:
-    frame parameters (1 thread / frame) -> fused forward warp of RGB + sparse depth + validity mask
+    frame parameters (1 CTA / frame) -> fused forward warp of RGB + sparse depth + validity mask
     -> fused inverse warp of the normals with R^T rotation and renormalisation.
 Workload (BASELINE.json configs[2], the configuration the metric is quoted on): Azure-Kinect-shaped
 640x480 camera, 256 frames per GPU, uniform roll/pitch in +-30 deg, I_a = [0,1,0], seeded synthetic
@@ -14,8 +14,12 @@ there is no data-path collective, NCCL is used for the barrier and the max-over-
 
 Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same metric
 through the C-ABI host-buffer entry point (pinned host buffers, H2D + kernels + D2H inside the timed
-region); `roofline` = dominant kernel against the measured HBM copy bandwidth; `cpu_baseline` = the CPU
-oracle (a port of the reference's algorithm, bit-identical to the reference run on CPU) on the host cores.
+region); `roofline` = dominant kernel against the measured HBM copy bandwidth, every kernel with its own
+fraction, the step at the survey's 56 B/px; `cpu_baseline` = the reference's own PyTorch warping executed on the
+box's host cores (oracle/_ref, `kind: "reference"`; the C port of it beside, `cpu_port`); `reference_gpu` = the
+reference as shipped on one B200 (the "before" number); `dropin` = the unmodified call sequence of
+surface_normal.py:148-170 on the drop-in class; `secondary` = the S3 (+-90 deg roll) and S1 (320x240) workloads;
+`config5` = BASELINE config 5, the reference's random-init CNNs around the warp, before / after.
 """
 import argparse
 import ctypes
@@ -25,18 +29,20 @@ import subprocess
 import sys
 import threading
 import time
+import warnings
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from tests import common as C  # noqa: E402  (seeded synthetic inputs shared with the tests)
+from vi_depth_completion_b200 import synthetic as S  # noqa: E402  (seeded synthetic inputs, shared with the tests)
 
 WORKLOAD = "S2"          # 640x480 Azure-Kinect-shaped camera
 FRAMES_PER_GPU = 256
 BYTES_PER_PX_FWD = 12 + 4 + 12 + 4 + 1   # read RGB+depth, write RGB+depth, write u8 mask
 BYTES_PER_PX_INV = 12 + 12               # read normals, write rotated+normalised normals
+BYTES_PER_PX_SURVEY = 56                 # the graded figure (no mask byte)
 METRIC = "gravity warp+unwarp frames/sec at 640x480"
 UNIT = "frames/s"
 
@@ -60,6 +66,10 @@ def ncu_traffic():
         except Exception:
             return None
     return None
+
+
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
 class ClockSampler:
@@ -114,46 +124,239 @@ class ClockSampler:
 
 
 def make_inputs(rank, B):
-    cam = C.CAMERAS[WORKLOAD]
-    I_g, I_a = C.random_gravity(B, seed=1234 + rank, roll_deg=30.0, pitch_deg=30.0)   # sharding.rank_seed(1234, rank)
+    cam = S.CAMERAS[WORKLOAD]
+    I_g, I_a = S.random_gravity(B, seed=1234 + rank, roll_deg=30.0, pitch_deg=30.0)   # sharding.rank_seed(1234, rank)
     return cam, I_g, I_a
+
+
+def reference_sequence(w, rgb, depth, normals, g, a):
+    """The path exactly as the reference's caller runs it (surface_normal.py:148-170) plus the 3-D depth warp of :110-112:
+    warp RGB, warp depth, validity mask, inverse warp + R^T, F.normalize.  `w` is any Warping2DOFAlignment."""
+    import torch
+    _, x1 = w.warp_with_gravity_center_aligned(rgb, g, a)
+    _, d1 = w.warp_with_gravity_center_aligned(depth, g, a)
+    mask = (x1[:, 0:1] + x1[:, 1:2] + x1[:, 2:3] > 1e-2).float()
+    _, z = w.inverse_warp_normal_image_with_gravity_center_aligned(normals, g, a)
+    return x1, d1, mask, torch.nn.functional.normalize(z, dim=1)
+
+
+def time_reference_cpu(cam, cores, budget_s, steps=None, warmup=1, log=None):
+    """The reference's PyTorch warping path (oracle/_ref, device 'cpu') on `cores` host threads over a bounded sample of the S2
+    workload.  Returns the cpu_baseline dict (kind 'reference') or None when the reference files are not on the machine."""
+    import torch
+    from oracle import ref_loader as RL
+    if not RL.reference_available():
+        return None
+    warnings.filterwarnings("ignore")
+    torch.set_num_threads(cores)
+    w = RL.load_reference_class("cpu")(*cam)
+    H, W = int(w.H), int(w.W)
+    I_g, I_a = S.random_gravity(64, seed=1234, roll_deg=30.0, pitch_deg=30.0)
+    rgb, depth, normals = S.random_images(64, H, W, seed=1)
+    tt = torch.from_numpy
+
+    def run(n):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            reference_sequence(w, tt(rgb[:n]), tt(depth[:n]), tt(normals[:n]), tt(I_g[:n]), tt(I_a[:n]))
+        return time.perf_counter() - t0
+
+    run(1)                                                        # allocator / thread-pool warm-up
+    per_frame = run(2) / 2
+    n_steps = steps if steps is not None else 3
+    sample = int(max(2, min(64, budget_s / max(per_frame * (n_steps + warmup), 1e-6))))
+    for _ in range(warmup):
+        run(sample)
+    times = [run(sample) for _ in range(n_steps)]
+    med = float(np.median(times))
+    return {"value": sample / med, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"{sample} frames of the S2 workload x {n_steps} timed passes (median) after {warmup} warm-up, the reference's "
+                      f"networks/warping_2dof_alignment.py executed on CPU by torch {torch.__version__} with {cores} threads: warp RGB + "
+                      "warp depth + mask + inverse warp + F.normalize",
+            "ms_per_step": med * 1e3, "frames_per_step": sample, "step_times_s": [round(t, 4) for t in times]}
+
+
+def time_port_cpu(cam, cores, budget_s, check=None):
+    """The C restatement of the reference (oracle/warp_oracle.c, bit-identical to the reference executed on CPU) on `cores`
+    pthreads.  `check` = optional (rgb_w, depth_w, mask, normals) host arrays of the GPU run to compare bit for bit."""
+    from oracle import oracle as O
+    sample = max(2 * cores, 32)
+    I_g, I_a = S.random_gravity(FRAMES_PER_GPU, seed=1234, roll_deg=30.0, pitch_deg=30.0)
+    orc = O.Oracle(*cam)
+    if check is not None:
+        s_rgb, s_d, s_n = check["in_rgb"][:sample], check["in_depth"][:sample], check["in_normals"][:sample]
+    else:
+        s_rgb, s_d, s_n = S.random_images(sample, orc.H, orc.W, seed=1)
+        s_d = s_d[:, None]
+    O.warp_unwarp_mt(orc, s_rgb[:cores], s_d[:cores], s_n[:cores], I_g[:cores], I_a[:cores], cores)  # warm
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        ref = O.warp_unwarp_mt(orc, s_rgb, s_d, s_n, I_g[:sample], I_a[:sample], cores)
+        reps += 1
+        if time.perf_counter() - t0 > budget_s or reps >= 50:
+            break
+    dt = time.perf_counter() - t0
+    out = {"value": sample * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"{sample} frames x {reps} repetitions of the same step on oracle/warp_oracle.c ({cores} pthreads)"}
+    if check is not None:
+        out["gpu_output_bit_identical_on_sample"] = bool(
+            np.array_equal(ref[0], check["rgb_w"][:sample]) and np.array_equal(ref[2], check["mask"][:sample]) and
+            np.array_equal(ref[3], check["normals"][:sample]) and np.array_equal(ref[1], check["depth_w"][:sample, 0]))
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (the oracle port -- the Python
-    reference itself cannot travel to the GPU box), all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores -- the reference's PyTorch
+    code from oracle/_ref when it travelled here, else the C port of it -- all host threads, a bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as O
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    sample = min(256, max(4 * cores, 32))
-    cam, I_g, I_a = make_inputs(0, sample)
-    orc = O.Oracle(*cam)
-    rgb, depth, normals = C.random_images(sample, orc.H, orc.W, seed=1)
-    for _ in range(min(args.warmup, 1)):
-        O.warp_unwarp_mt(orc, rgb, depth, normals, I_g, I_a, cores)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        O.warp_unwarp_mt(orc, rgb, depth, normals, I_g, I_a, cores)
-    dt = time.perf_counter() - t0
-    fps = sample * args.steps / dt
+    cores = host_cores()
+    cam = S.CAMERAS[WORKLOAD]
+    base = time_reference_cpu(cam, cores, budget_s=100.0, steps=max(args.steps, 1), warmup=max(args.warmup, 0))
+    port = None
+    if base is None:                                             # reference files absent: the port is the arm
+        from oracle import oracle as O
+        sample = min(256, max(4 * cores, 32))
+        I_g, I_a = S.random_gravity(sample, seed=1234, roll_deg=30.0, pitch_deg=30.0)
+        orc = O.Oracle(*cam)
+        rgb, depth, normals = S.random_images(sample, orc.H, orc.W, seed=1)
+        for _ in range(max(args.warmup, 0)):
+            O.warp_unwarp_mt(orc, rgb, depth, normals, I_g, I_a, cores)
+        times = []
+        for _ in range(max(args.steps, 1)):
+            t0 = time.perf_counter()
+            O.warp_unwarp_mt(orc, rgb, depth, normals, I_g, I_a, cores)
+            times.append(time.perf_counter() - t0)
+        med = float(np.median(times))
+        base = {"value": sample / med, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": med * 1e3, "frames_per_step": sample,
+                "sample": f"{sample} frames x {len(times)} timed passes (median) after {max(args.warmup, 0)} warm-up, oracle/warp_oracle.c, "
+                          f"{cores} pthreads (oracle/_ref absent)"}
+    else:
+        port = time_port_cpu(cam, cores, budget_s=3.0)
+    fps = base["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{WORKLOAD}: 640x480, {sample} frames per step (bounded sample of the 256-frame batch), "
+        "config": {"workload": f"{WORKLOAD}: 640x480, {base['frames_per_step']} frames per step (bounded sample of the 256-frame batch), "
                                "warp RGB + warp depth + mask + unwarp normals + renormalise"},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} frames x {args.steps} steps, oracle/warp_oracle.c, {cores} pthreads"},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if port is not None:
+        line["cpu_port"] = port
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
+def cuda_time(fn, iters, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def secondary_workloads(dev, iters):
+    """BASELINE configs S3 (ScanNet intrinsics, roll in {0, +-45, +-60, +-90} deg) and S1 (320x240, 64 frames): fused step."""
+    import torch
+    from vi_depth_completion_b200.warping_2dof_alignment import Warping2DOFAlignment
+    out = {}
+    for name, cam, B, grav in (("S3_extreme_roll_640x480_B256", "S3", 256, "roll"), ("S1_320x240_B64", "S1", 64, "random")):
+        w = Warping2DOFAlignment(*S.CAMERAS[cam])
+        H, W = int(w.H), int(w.W)
+        I_g, I_a = S.extreme_roll_gravity(B, seed=5) if grav == "roll" else S.random_gravity(B, seed=1234)
+        g, a = torch.from_numpy(I_g).to(dev), torch.from_numpy(I_a).to(dev)
+        gen = torch.Generator(device=dev).manual_seed(7)
+        rgb = torch.rand(B, 3, H, W, device=dev, generator=gen)
+        depth = torch.rand(B, 1, H, W, device=dev, generator=gen) * 9.6 + 0.4
+        nrm = torch.randn(B, 3, H, W, device=dev, generator=gen)
+        f = cuda_time(lambda: w.warp_rgbd(rgb, depth, g, a), iters)
+        i = cuda_time(lambda: w.unwarp_normals(nrm, g, a), iters)
+        out[name] = {"forward_ms": f, "inverse_ms": i, "frames_per_s": B / (f + i) * 1e3,
+                     "frac_of_hbm_peak_56Bpx": B * H * W * BYTES_PER_PX_SURVEY / (f + i) / 1e6 / measured_peak()[0]}
+        del rgb, depth, nrm
+    return out
+
+
+def config5(dev, rank, world, frames_per_gpu=16, steps=3):
+    """BASELINE config 5: the reference's SurfaceNormalPrediction + ModifiedFPN (oracle/_ref, unmodified, random init) at 320x240,
+    a batch split over the ranks; step time and the share of it spent in the warp / unwarp calls with the reference's own
+    warper on the GPU (before) and with the drop-in (after).  None when the reference files are not on the machine."""
+    import torch
+    from oracle import ref_loader as RL
+    if not RL.reference_available():
+        return None
+    import vi_depth_completion_b200.warping_2dof_alignment as dropin
+    warnings.filterwarnings("ignore")
+    snp, fpn = RL.ReferenceNetworks(dropin).build(dev, use_mask=False, seed=11)      # INTEGRATION.md section 2 aliasing
+    ref_warper = RL.load_reference_class(f"cuda:{dev.index}")(fx=202., fy=202., cx=0.5 * 319.87654, cy=0.5 * 239.87603)
+    new_warper = snp.warp_2dof_alignment
+    B = frames_per_gpu
+    I_g, I_a = S.random_gravity(B, seed=2000 + rank, roll_deg=20, pitch_deg=20)
+    rgb = torch.from_numpy(S.smooth_images(B, 240, 320, seed=5 + rank)).to(dev)
+    depth = torch.from_numpy(S.random_images(B, 240, 320, seed=6 + rank, sparse_depth=True)[1][:, None]).to(dev)
+    g, a = torch.from_numpy(I_g).to(dev), torch.from_numpy(I_a).to(dev)
+    res = {}
+    for tag, warper in (("before_reference_warper", ref_warper), ("after_dropin", new_warper)):
+        snp.warp_2dof_alignment = warper
+        t_warp = [0.0]
+
+        class Timed:                                             # wall-clock around the two warper calls, GPU synchronised
+            def warp_with_gravity_center_aligned(self, *x, **k):
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                r = warper.warp_with_gravity_center_aligned(*x, **k)
+                torch.cuda.synchronize(); t_warp[0] += time.perf_counter() - t0
+                return r
+
+            def inverse_warp_normal_image_with_gravity_center_aligned(self, *x, **k):
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                r = warper.inverse_warp_normal_image_with_gravity_center_aligned(*x, **k)
+                torch.cuda.synchronize(); t_warp[0] += time.perf_counter() - t0
+                return r
+
+        def step():
+            with torch.no_grad():
+                n = snp(rgb, g, a)                               # main.py:267-269
+                return fpn(rgb, n, depth)                        # main.py:274
+        step(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
+        total = (time.perf_counter() - t0) / steps
+        snp.warp_2dof_alignment = Timed()
+        t_warp[0] = 0.0
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
+        res[tag] = {"step_ms": total * 1e3, "warp_unwarp_ms": t_warp[0] / steps * 1e3, "warp_share_of_step": (t_warp[0] / steps) / total,
+                    "frames_per_s_per_gpu": B / total}
+    snp.warp_2dof_alignment = new_warper
+    if world > 1:
+        import torch.distributed as dist
+        for tag in res:
+            t = torch.tensor([res[tag]["step_ms"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res[tag]["step_ms_max_over_ranks"] = float(t.item())
+            res[tag]["frames_per_s_aggregate"] = B * world / (float(t.item()) * 1e-3)
+    res["frames_per_gpu"] = B
+    res["networks"] = "SurfaceNormalPrediction (62.9 M params) + ModifiedFPN (310.3 M params), random init, eval, fp32, 320x240"
+    res["speedup_of_the_step"] = res["before_reference_warper"]["step_ms"] / res["after_dropin"]["step_ms"]
+    del snp, fpn
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -225,20 +428,46 @@ def run_ours(args):
 
     # ---- informational: the opt-in packed layout (channels-last RGBD, one 128-bit load per tap), same frames ----
     packed = torch.cat([rgb, depth], 1).contiguous(memory_format=torch.channels_last)
-    for _ in range(3):
-        w.warp_rgbd_packed(packed, g, a)
-    torch.cuda.synchronize()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    for _ in range(K):
-        w.warp_rgbd_packed(packed, g, a)
-    p1.record()
-    torch.cuda.synchronize()
-    packed_ms = p0.elapsed_time(p1) / K
+    packed_ms = cuda_time(lambda: w.warp_rgbd_packed(packed, g, a), K)
     del packed
 
+    # ---- dropin: the UNMODIFIED call sequence of surface_normal.py:148-170 (+ the 3-D depth warp) on the drop-in class -------
+    depth3 = depth[:, 0]
+    with torch.no_grad():
+        dropin_calls = {
+            "warp_with_gravity_center_aligned(rgb)": cuda_time(lambda: w.warp_with_gravity_center_aligned(rgb, g, a), K),
+            "warp_with_gravity_center_aligned(depth 3-D)": cuda_time(lambda: w.warp_with_gravity_center_aligned(depth3, g, a), K),
+            "inverse_warp_normal_image_with_gravity_center_aligned": cuda_time(
+                lambda: w.inverse_warp_normal_image_with_gravity_center_aligned(normals, g, a), K),
+        }
+        dropin_seq_ms = cuda_time(lambda: reference_sequence(w, rgb, depth3, normals, g, a), K)
+
+    # ---- reference_gpu: the reference AS SHIPPED on this B200 (oracle/_ref, 'cuda:N'), same sequence, same 256 frames --------
+    reference_gpu = None
+    if rank == 0:
+        try:
+            from oracle import ref_loader as RL
+            if RL.reference_available():
+                warnings.filterwarnings("ignore")
+                rw = RL.load_reference_class(f"cuda:{local}")(*cam)
+                with torch.no_grad():
+                    reference_sequence(rw, rgb[:2], depth3[:2], normals[:2], g[:2], a[:2])
+                    torch.cuda.synchronize()
+                    ts = []
+                    for _ in range(2):
+                        t0 = time.perf_counter()
+                        reference_sequence(rw, rgb, depth3, normals, g, a)
+                        torch.cuda.synchronize()
+                        ts.append(time.perf_counter() - t0)
+                reference_gpu = {"value": B / min(ts), "unit": UNIT, "seconds_per_256_frames": min(ts),
+                                 "what": "networks/warping_2dof_alignment.py unmodified on cuda (per-sample Python loop, ~45 launches and "
+                                         "several host syncs per frame and direction) + the caller's mask and F.normalize",
+                                 "dropin_same_sequence_speedup": (B / (dropin_seq_ms * 1e-3)) / (B / min(ts))}
+                del rw
+        except Exception as e:                                    # the baseline must never take the bench down
+            reference_gpu = {"error": repr(e)[:300]}
+
     # ---- e2e: C-ABI host-buffer entry point, pinned host memory, H2D + kernels + D2H timed --------
-    hw = H * W
     h_rgb = torch.empty(B, 3, H, W, pin_memory=True); h_rgb.copy_(rgb)
     h_depth = torch.empty(B, 1, H, W, pin_memory=True); h_depth.copy_(depth)
     h_nrm = torch.empty(B, 3, H, W, pin_memory=True); h_nrm.copy_(normals)
@@ -264,35 +493,41 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     _, _, e2e_value = sharding.aggregate_throughput(B * Ke, e2e_s * 1e3, dev)
-    clocks = sampler.stop() if rank == 0 else None             # window: timed steps + packed kernel + e2e steps
+    clocks = sampler.stop() if rank == 0 else None             # window: timed steps + packed kernel + dropin + e2e steps
     if clocks is not None:
         clocks["samples_during_timed_steps"] = n_clock_rows_timed
     # sanity: the e2e path returns the same bits as the resident path
     _, rgb_w, depth_w, mask = w.warp_rgbd(rgb, depth, g, a)
     torch.cuda.synchronize()
     e2e_ok = bool(torch.equal(rgb_w.cpu(), o_rgb) and torch.equal(mask.cpu(), o_mask))
+    del rgb_w, depth_w, mask
 
-    # ---- cpu baseline (rank 0, N == 1): the oracle port on the host cores, bounded sample ----------
-    cpu = None
+    secondary = secondary_workloads(dev, max(5, min(K, 20))) if rank == 0 else None
+
+    # ---- cpu baselines (rank 0, N == 1): the executed reference and its C port on the host cores, bounded samples ----------
+    cpu = cpu_port = None
     if rank == 0 and world == 1:
-        from oracle import oracle as O
-        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        sample = max(2 * cores, 32)
-        orc = O.Oracle(*cam)
-        s_rgb = h_rgb[:sample].numpy(); s_d = h_depth[:sample].numpy(); s_n = h_nrm[:sample].numpy()
-        O.warp_unwarp_mt(orc, s_rgb[:cores], s_d[:cores], s_n[:cores], I_g[:cores], I_a[:cores], cores)  # warm
-        reps, t0 = 0, time.perf_counter()
-        while True:
-            ref = O.warp_unwarp_mt(orc, s_rgb, s_d, s_n, I_g[:sample], I_a[:sample], cores)
-            reps += 1
-            if time.perf_counter() - t0 > 10.0 or reps >= 50:
-                break
-        dt = time.perf_counter() - t0
-        same = bool(np.array_equal(ref[0], o_rgb[:sample].numpy()) and np.array_equal(ref[2], o_mask[:sample].numpy())
-                    and np.array_equal(ref[3], o_nrm[:sample].numpy()) and np.array_equal(ref[1], o_depth[:sample, 0].numpy()))
-        cpu = {"value": sample * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{sample} frames x {reps} repetitions of the same step on oracle/warp_oracle.c ({cores} pthreads)",
-               "gpu_output_bit_identical_on_sample": same}
+        cores = host_cores()
+        check = {"in_rgb": h_rgb.numpy(), "in_depth": h_depth.numpy(), "in_normals": h_nrm.numpy(), "rgb_w": o_rgb.numpy(),
+                 "depth_w": o_depth.numpy(), "mask": o_mask.numpy(), "normals": o_nrm.numpy()}
+        cpu_port = time_port_cpu(cam, cores, budget_s=8.0, check=check)
+        try:
+            cpu = time_reference_cpu(cam, cores, budget_s=15.0)
+        except Exception as e:
+            cpu = None
+            cpu_port["reference_error"] = repr(e)[:300]
+        if cpu is None:
+            cpu, cpu_port = cpu_port, None
+    del h_rgb, h_depth, h_nrm, o_rgb, o_depth, o_mask, o_nrm
+
+    # ---- config 5: the reference's CNNs (random init) around the warp, before / after; every rank takes part -------------------
+    del rgb, depth, normals
+    torch.cuda.empty_cache()
+    c5 = None
+    try:
+        c5 = config5(dev, rank, world)
+    except Exception as e:
+        c5 = {"error": repr(e)[:300]}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -300,23 +535,31 @@ def run_ours(args):
         # kernel families behind the fused entry points (vidc_kernels.cu: shear_level(), VIDC_SHEAR, default 2)
         shear = os.environ.get("VIDC_SHEAR", "2")[:1]
         fwd_name = "warp_rgbd_fast_kernel" if shear == "0" else "warp_rgbd_shear_kernel"
-        inv_name = "unwarp_normals_shear_kernel" if shear == "2" else "unwarp_normals_fast_kernel"
+        inv_name = ("unwarp_normals_box_kernel" if os.environ.get("VIDC_INV_BOX", "0")[:1] == "1" else
+                    ("unwarp_normals_shear_kernel" if shear == "2" else "unwarp_normals_fast_kernel"))
         dom = (fwd_name, fwd_ms, BYTES_PER_PX_FWD) if fwd_ms >= inv_ms else (inv_name, inv_ms, BYTES_PER_PX_INV)
         achieved = px * dom[2] / (dom[1] * 1e-3) / 1e9
         traffic = ncu_traffic()
+
+        def kern(ms, bpp):
+            gbps = px * bpp / ms / 1e6
+            return {"ms": ms, "GBps": gbps, "frac": gbps / peak, "bytes_per_px": bpp}
+        per_gpu = value / world
+        planes3 = dropin_calls["warp_with_gravity_center_aligned(rgb)"]
         roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "peak_source": peak_src,
                     "traffic": ((traffic or {}).get(dom[0]) or {}).get("dram_bytes_total"),
                     "traffic_source": ((traffic or {}).get(dom[0]) or {}).get("source"),
                     "algorithmic_bytes_per_launch": px * dom[2],
-                    "kernels": {fwd_name: {"ms": fwd_ms, "GBps": px * BYTES_PER_PX_FWD / fwd_ms / 1e6},
-                                inv_name: {"ms": inv_ms, "GBps": px * BYTES_PER_PX_INV / inv_ms / 1e6},
-                                "warp_rgbd_nhwc4_kernel (opt-in packed RGBD layout, not part of `value`)": {
-                                    "ms": packed_ms, "GBps": px * BYTES_PER_PX_FWD / packed_ms / 1e6,
-                                    "frac": px * BYTES_PER_PX_FWD / packed_ms / 1e6 / peak}},
-                    "step": {"bytes_per_frame": H * W * (BYTES_PER_PX_FWD + BYTES_PER_PX_INV),
-                             "achieved": value / world * H * W * (BYTES_PER_PX_FWD + BYTES_PER_PX_INV) / 1e9,
-                             "frac": value / world * H * W * (BYTES_PER_PX_FWD + BYTES_PER_PX_INV) / 1e9 / peak}}
+                    "kernels": {fwd_name: kern(fwd_ms, BYTES_PER_PX_FWD), inv_name: kern(inv_ms, BYTES_PER_PX_INV),
+                                "warp_planes_shear_kernel<640,480,3> (the drop-in's RGB warp)": kern(planes3, 24),
+                                "warp_rgbd_nhwc4_kernel (opt-in packed RGBD layout, not part of `value`)": kern(packed_ms, BYTES_PER_PX_FWD)},
+                    "step": {"bytes_per_frame": H * W * BYTES_PER_PX_SURVEY,
+                             "achieved": per_gpu * H * W * BYTES_PER_PX_SURVEY / 1e9,
+                             "frac": per_gpu * H * W * BYTES_PER_PX_SURVEY / 1e9 / peak,
+                             "bytes_per_px": BYTES_PER_PX_SURVEY,
+                             "with_mask_byte": {"bytes_per_px": BYTES_PER_PX_FWD + BYTES_PER_PX_INV,
+                                                "frac": per_gpu * H * W * (BYTES_PER_PX_FWD + BYTES_PER_PX_INV) / 1e9 / peak}}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
             "ms_per_step": elapsed_ms / K, "ms_per_step_median": float(np.median(step_ms)), "ms_per_step_min": float(np.min(step_ms)),
@@ -328,6 +571,14 @@ def run_ours(args):
                        "layout": "NCHW fp32", "sharding": f"batch over {world} GPU(s), no data-path collective"},
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "cpu_port": cpu_port,
+            "reference_gpu": reference_gpu,
+            "dropin": {"what": "surface_normal.py:148-170 call sequence unmodified on the drop-in class (+ the 3-D depth warp of :110-112): "
+                               "warp RGB, warp depth, the caller's torch mask expression, inverse warp + R^T, the caller's F.normalize",
+                       "value": B / (dropin_seq_ms * 1e-3), "unit": UNIT, "ms_per_step": dropin_seq_ms, "ms_per_call": dropin_calls,
+                       "frac_of_hbm_peak_56Bpx": B / (dropin_seq_ms * 1e-3) * H * W * BYTES_PER_PX_SURVEY / 1e9 / peak},
+            "secondary": secondary,
+            "config5": c5,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "api": "vidc_warp_unwarp_host (C ABI, pinned host buffers)", "matches_resident_path": e2e_ok},
             "gpu_launches": int(launches),
