@@ -79,7 +79,8 @@ typedef struct vidc_frame_params {
     float inv_col_major;   /* same for the inverse warp */
     float reserved[11];    /* [0..9]: bit t set = 32x32 canvas tile t (row-major, <= 320 tiles) certainly lies outside the source
                               footprint of the forward warp -- written by the forward entry points, zero from every other
-                              producer; [10]: zero */
+                              producer; [10]: 1.0 when the shared-reciprocal division of the inverse warp is provably exact for
+                              every pixel of the frame (written by the inverse entry points' per-frame kernel), else 0 */
 } vidc_frame_params;
 
 /* Logical (N, C, H, W) image batch with element strides.  N <= 65535 frames per call (they ride on gridDim.z); one

@@ -20,7 +20,10 @@ __global__ void frame_params_kernel(vidc_camera cam, const float* __restrict__ I
     p.fwd_col_major = fabsf(p.Hinv[1] * p.ikh) > 4.0f * fabsf(p.Hinv[0] * p.ikw) ? 1.0f : 0.0f;
     p.inv_col_major = fabsf(p.H[1]) > 4.0f * fabsf(p.H[0]) ? 1.0f : 0.0f;
 #pragma unroll
-    for (int k = 0; k < 11; ++k) p.reserved[k] = 0.0f;
+    for (int k = 0; k < 10; ++k) p.reserved[k] = 0.0f;
+    // reserved[10]: 1.0 when the inverse warp's shared-reciprocal division is provably exact for every pixel of this frame
+    // (vidc::inv_division_proven) -- the inverse kernels then skip their per-pixel window test
+    p.reserved[10] = vidc::inv_division_proven(p, cam) ? 1.0f : 0.0f;
     out[i] = p;
     if (H_out) {                       // the Cg_H_C every reference method returns (:153-156, :255)
 #pragma unroll

@@ -349,7 +349,7 @@ warp_planes_shear_kernel(const __grid_constant__ PlanesArgs a) {
 // ---- inverse: camera px -> canvas coords, 3 planes, R^T, renormalisation ------------------------------------------------
 // The fourth component of the staging slot carries the optional validity flag.
 template <int GW, int GH, bool NORMALIZE, bool HAS_VALID, bool ALONG_Y>
-__device__ __forceinline__ void unwarp_normals_shear_segments(const InvArgs& a, const float* pr, float4 (*tile)[32], int sh_l) {
+__device__ __forceinline__ void unwarp_normals_shear_segments(const InvArgs& a, const float* pr, float4 (*tile)[32], int sh_l, bool proven) {
     const int W = GW ? GW : a.cam.W, H = GW ? GH : a.cam.H;
     const int b = blockIdx.z, lane = threadIdx.x, warp = threadIdx.y;
     const int tileX0 = blockIdx.x * TILE_W, tileY0 = blockIdx.y * TILE_H;
@@ -376,7 +376,7 @@ __device__ __forceinline__ void unwarp_normals_shear_segments(const InvArgs& a, 
             v = fmaf(Hm[4], Yf, v0) + Hm[5];
         }
         float tx, ty;
-        div2_rn(u, v, s, tx, ty);                                  // :245
+        div2_sel(u, v, s, proven, tx, ty);                         // :245 (window test only for frames that did not pass the proof)
         const float cxp = kw * (tx - px_min);
         const float cyp = kh * (ty - py_min);
         const float gx = a.cam.inv_half_w * (cxp - a.cam.cx);
@@ -437,13 +437,14 @@ unwarp_normals_shear_kernel(const __grid_constant__ InvArgs a) {
         const float vc = fmaf(Hm[4], yc, Hm[3] * xc) + Hm[5], sc = fmaf(Hm[7], yc, Hm[6] * xc) + Hm[8];
         along_y = shear_of_tile(Hm[3] * sc - vc * Hm[6], Hm[4] * sc - vc * Hm[7], lane, sh_l);
     }
+    const bool proven = __ldg(&a.prm[b].reserved[10]) != 0.0f;     // CTA-uniform (vidc::inv_division_proven)
     if (along_y) {                                                 // CTA-uniform; the common orientation stays straight-line
-        unwarp_normals_shear_segments<GW, GH, NORMALIZE, HAS_VALID, true>(a, pr, tile, sh_l);
+        unwarp_normals_shear_segments<GW, GH, NORMALIZE, HAS_VALID, true>(a, pr, tile, sh_l, proven);
         __syncthreads();
         unwarp_normals_shear_write_out<GW, GH, HAS_VALID, true>(a, tile);
         return;
     }
-    unwarp_normals_shear_segments<GW, GH, NORMALIZE, HAS_VALID, false>(a, pr, tile, sh_l);
+    unwarp_normals_shear_segments<GW, GH, NORMALIZE, HAS_VALID, false>(a, pr, tile, sh_l, proven);
     __syncthreads();
     unwarp_normals_shear_write_out<GW, GH, HAS_VALID, false>(a, tile);
 }
