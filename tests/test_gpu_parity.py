@@ -169,6 +169,42 @@ def test_coverage_counts(cuda_device, oracle_mod):
     assert np.array_equal(cov.cpu().numpy(), mask.cpu().numpy().reshape(5, -1).sum(1))
 
 
+def test_feature_maps_with_more_than_four_channels(cuda_device, oracle_mod):
+    """F.grid_sample takes any channel count: the drop-in warps a 7-channel map in plane groups (same frame parameters) and
+    back-propagates through it, bit-identical to the oracle per channel / equal to the 3-channel gradients."""
+    w, o = _mk("S1", cuda_device)
+    B = 3
+    I_g, I_a = C.random_gravity(B, seed=21)
+    x = np.random.RandomState(4).rand(B, 7, 240, 320).astype(np.float32)
+    g, a = torch.from_numpy(I_g).to(cuda_device), torch.from_numpy(I_a).to(cuda_device)
+    for mode in ("bilinear", "nearest"):
+        _, y = w.warp_with_gravity_center_aligned(torch.from_numpy(x).to(cuda_device), g, a, interp_mode=mode)
+        _, oy = o.warp_with_gravity_center_aligned(x, I_g, I_a, interp_mode=mode)
+        assert y.shape == (B, 7, 240, 320) and C.count_bit_mismatches(y.cpu().numpy(), oy) == 0
+    xt = torch.from_numpy(x).to(cuda_device).requires_grad_(True)
+    wt = torch.from_numpy(np.random.RandomState(5).randn(B, 7, 240, 320).astype(np.float32)).to(cuda_device)
+    (w.warp_with_gravity_center_aligned(xt, g, a)[1] * wt).sum().backward()
+    x3 = torch.from_numpy(x[:, 4:7].copy()).to(cuda_device).requires_grad_(True)
+    (w.warp_with_gravity_center_aligned(x3, g, a)[1] * wt[:, 4:7]).sum().backward()
+    assert torch.allclose(xt.grad[:, 4:7], x3.grad, rtol=0, atol=2e-5)     # atomics: rounding-level differences only
+
+
+def test_alignment_batch_must_match(cuda_device):
+    """a shorter I_a used to be read out of bounds.  The reference fails at I_a[i] (:41, IndexError) or at the
+    batched product I_a @ I_g (:43, RuntimeError); so does the drop-in, before any kernel sees the pointers."""
+    w, _ = _mk("S1", cuda_device)
+    g = torch.zeros(4, 3, device=cuda_device); g[:, 1] = 1
+    img = torch.zeros(4, 3, 240, 320, device=cuda_device)
+    with pytest.raises(IndexError):
+        w.warp_with_gravity_center_aligned(img, g, g[:1])
+    with pytest.raises(RuntimeError):
+        w.inverse_warp_normal_image_with_gravity_center_aligned(img, g[:2], g)      # I_a longer than I_g ... and x.shape[0] != B
+    with pytest.raises(RuntimeError):
+        w._build_homography(g[:3], g)
+    with pytest.raises(RuntimeError):
+        w.warp_rgbd(img, None, g.reshape(2, 6), g)
+
+
 def test_errors(cuda_device):
     w, _ = _mk("S1", cuda_device)
     g = torch.zeros(2, 3, device=cuda_device); g[:, 1] = 1

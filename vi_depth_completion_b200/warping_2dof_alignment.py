@@ -81,12 +81,17 @@ class _WarpFn(torch.autograd.Function):
         w = ctx.warper
         B, C, Hin, Win = ctx.in_shape
         grad = grad.float()
-        gx = torch.empty((B, C, Hin, Win), dtype=torch.float32, device=grad.device)
-        gi = _image(grad)
-        with torch.cuda.device(grad.device):
-            check(lib().vidc_warp_backward(ctypes.byref(w._cam), ctypes.byref(gi), g.data_ptr(), a.data_ptr(), g.shape[0],
-                                           1 if ctx.inverse else 0, ctx.mode, w._params_ws(g.shape[0], grad.device).data_ptr(),
-                                           gx.data_ptr(), Hin, Win, _stream_ptr(grad.device)))
+        groups = []
+        for c0 in range(0, C, 4):                              # feature maps: the scatter kernel takes <= 4 planes per call
+            gc = grad[:, c0:c0 + 4]
+            gxc = torch.empty((B, gc.shape[1], Hin, Win), dtype=torch.float32, device=grad.device)
+            gi = _image(gc)
+            with torch.cuda.device(grad.device):
+                check(lib().vidc_warp_backward(ctypes.byref(w._cam), ctypes.byref(gi), g.data_ptr(), a.data_ptr(), g.shape[0],
+                                               1 if ctx.inverse else 0, ctx.mode, w._params_ws(g.shape[0], grad.device).data_ptr(),
+                                               gxc.data_ptr(), Hin, Win, _stream_ptr(grad.device)))
+            groups.append(gxc)
+        gx = groups[0] if len(groups) == 1 else torch.cat(groups, 1)
         return gx, None, None, None, None, None, None
 
 
@@ -302,11 +307,13 @@ class Warping2DOFAlignment:
         if x.dim() != 4:
             raise RuntimeError(f"x: expected a 4-D tensor, got {x.dim()}-D")
         device = x.device
-        Hm = torch.as_tensor(np.asarray(Cg_H_C.detach().cpu() if isinstance(Cg_H_C, torch.Tensor) else Cg_H_C,
-                                        dtype=np.float32)).reshape(-1, 3, 3)
+        if isinstance(Cg_H_C, torch.Tensor):                    # stays on its device: no host round trip, no synchronisation
+            Hm = Cg_H_C.detach().to(device=device, dtype=torch.float32).reshape(-1, 3, 3)
+        else:
+            Hm = torch.as_tensor(np.asarray(Cg_H_C, dtype=np.float32)).reshape(-1, 3, 3).to(device)
         if Hm.shape[0] == 1 and x.shape[0] > 1:
             Hm = Hm.expand(x.shape[0], 3, 3)
-        Hd = Hm.contiguous().to(device)
+        Hd = Hm.contiguous()
         y = self._empty_like_canvas(x)
         xi, yi = _image(x), _image(y)
         with torch.cuda.device(device):
