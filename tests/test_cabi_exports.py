@@ -81,3 +81,20 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"(from|import)\s+oracle|#include\s+\".*oracle|libwarp_oracle", text), f
+
+
+def test_torch_extension_builds_and_registers_its_operators():
+    """The thin torch C++ extension in front of the C ABI (csrc/torch_ops.cpp): loads on a CPU-only box, registers the four
+    operators with CUDA and Meta kernels; shapes come out of the Meta kernels without a GPU."""
+    import torch
+    from vi_depth_completion_b200 import build as vb
+    torch.ops.load_library(vb.build_torch_ops())
+    x = torch.empty(2, 3, 240, 320, device="meta")
+    g = torch.empty(2, 3, device="meta")
+    H, y = torch.ops.vidc.warp_forward(x, g, g, 202., 202., 159.93827, 119.938015, 0)
+    assert H.shape == (2, 3, 3) and y.shape == (2, 3, 240, 320)
+    H, z = torch.ops.vidc.unwarp_normals(x, g, g, 404., 404., 319.87654, 239.87603, True)
+    assert z.shape == (2, 3, 480, 640)
+    outs = torch.ops.vidc.warp_rgbd(x, x[:, :1], g, g, 202., 202., 159.93827, 119.938015, 1)
+    assert [tuple(o.shape) for o in outs] == [(2, 3, 3), (2, 3, 240, 320), (2, 1, 240, 320), (2, 1, 240, 320)] and outs[3].dtype == torch.uint8
+    assert len(torch.ops.vidc.build_homography(g, g, 202., 202., 159.93827, 119.938015)) == 3

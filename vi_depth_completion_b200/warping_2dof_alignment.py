@@ -20,7 +20,7 @@ import ctypes
 import numpy as np
 import torch
 
-from . import _cabi
+from . import _cabi, _torchops
 from ._cabi import VidcCamera, VidcImage, check, lib
 
 __all__ = ["Warping2DOFAlignment"]
@@ -117,6 +117,16 @@ def _attach(x, out, warper=None, g=None, a=None, inverse=False, mode=0):
     return out
 
 
+def _op(fn, *args):
+    """Call a torch.ops.vidc operator; the C ABI's batch-mismatch status is the reference's `assert` (:123, :224)."""
+    try:
+        return fn(*args)
+    except RuntimeError as e:
+        if "vidc_b200 batch mismatch" in str(e):
+            raise AssertionError(str(e).split("vidc_b200 batch mismatch: ", 1)[-1].splitlines()[0]) from None
+        raise
+
+
 _MODES = {"bilinear": _cabi.VIDC_BILINEAR, "nearest": _cabi.VIDC_NEAREST, "bicubic": _cabi.VIDC_BICUBIC}
 
 
@@ -148,6 +158,7 @@ class Warping2DOFAlignment:
         self.device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
         self._const_cache = {}
         self._ws_bytes = {}
+        self._intr = (float(fx), float(fy), float(cx), float(cy))      # operator arguments of the torch C++ front end
 
     # ---- constant tensors the reference exposes as attributes (:15-24), built lazily ----------
     def _const(self, name):
@@ -192,6 +203,9 @@ class Warping2DOFAlignment:
 
     # networks/warping_2dof_alignment.py:35-58
     def _build_homography(self, I_g, I_a):
+        ops = _torchops.ops()
+        if ops is not None and isinstance(I_g, torch.Tensor) and isinstance(I_a, torch.Tensor):
+            return _op(ops.build_homography, I_g, I_a, *self._intr)
         _require_cuda_f32(I_g, "I_g")
         device = I_g.device
         g, a = _gravity(I_g, I_a, device)
@@ -231,16 +245,23 @@ class Warping2DOFAlignment:
             raise RuntimeError(f"x: expected a 3-D or 4-D tensor, got {x.dim()}-D")
         mode = _check_interp_mode(interp_mode, allow_bicubic=True)
         device = x.device
-        g, a = _gravity(I_g, I_a, device)
-        y = self._empty_like_canvas(x)
-        Cg_H_C = torch.empty((g.shape[0], 3, 3), dtype=torch.float32, device=device)
-        xi, yi = _image(x), _image(y)
-        with torch.cuda.device(device):
-            check(lib().vidc_warp_forward(ctypes.byref(self._cam), ctypes.byref(xi), g.data_ptr(), a.data_ptr(), g.shape[0],
-                                          mode, self._params_ws(g.shape[0], device).data_ptr(), Cg_H_C.data_ptr(),
-                                          ctypes.byref(yi), _stream_ptr(device)))
+        ops = _torchops.ops()
+        needs_graph = torch.is_grad_enabled() and x.requires_grad
+        if ops is not None and isinstance(I_g, torch.Tensor) and isinstance(I_a, torch.Tensor):
+            Cg_H_C, y = _op(ops.warp_forward, x, I_g, I_a, *self._intr, mode)          # thin torch C++ extension
+            g, a = _gravity(I_g, I_a, device) if needs_graph else (None, None)
+        else:
+            g, a = _gravity(I_g, I_a, device)
+            y = self._empty_like_canvas(x)
+            Cg_H_C = torch.empty((g.shape[0], 3, 3), dtype=torch.float32, device=device)
+            xi, yi = _image(x), _image(y)
+            with torch.cuda.device(device):
+                check(lib().vidc_warp_forward(ctypes.byref(self._cam), ctypes.byref(xi), g.data_ptr(), a.data_ptr(), g.shape[0],
+                                              mode, self._params_ws(g.shape[0], device).data_ptr(), Cg_H_C.data_ptr(),
+                                              ctypes.byref(yi), _stream_ptr(device)))
         # the scatter kernel of vidc_warp_backward covers bilinear and nearest; bicubic is forward-only
-        y = _attach(x, y) if mode == _cabi.VIDC_BICUBIC else _attach(x, y, self, g, a, False, mode)
+        if needs_graph:
+            y = _attach(x, y) if mode == _cabi.VIDC_BICUBIC else _attach(x, y, self, g, a, False, mode)
         if flag_fix_return:                                     # :153-154
             return Cg_H_C, y.view(x.shape[0], y.shape[2], y.shape[3])
         return Cg_H_C, y
@@ -269,6 +290,13 @@ class Warping2DOFAlignment:
         if x.dim() != 4:
             raise RuntimeError(f"x: expected a 4-D tensor, got {x.dim()}-D")
         device = x.device
+        ops = _torchops.ops()
+        if ops is not None and not want_valid and isinstance(I_g, torch.Tensor) and isinstance(I_a, torch.Tensor):
+            Cg_H_C, z = _op(ops.unwarp_normals, x, I_g, I_a, *self._intr, bool(normalize))   # thin torch C++ extension
+            if torch.is_grad_enabled() and x.requires_grad:
+                g, a = _gravity(I_g, I_a, device)
+                z = _attach(x, z, self, g, a, True, _cabi.VIDC_BILINEAR) if not normalize else _attach(x, z)
+            return Cg_H_C, z, None
         g, a = _gravity(I_g, I_a, device)
         z = self._empty_like_canvas(x)
         Cg_H_C = torch.empty((g.shape[0], 3, 3), dtype=torch.float32, device=device)
@@ -329,6 +357,15 @@ class Warping2DOFAlignment:
         _check_interp_mode(depth_mode)
         _require_cuda_f32(x_rgb, "x_rgb")
         device = x_rgb.device
+        ops = _torchops.ops()
+        if (ops is not None and with_mask and not with_coverage and isinstance(x_depth, torch.Tensor) and x_rgb.dim() == 4
+                and isinstance(I_g, torch.Tensor) and isinstance(I_a, torch.Tensor)):
+            d4 = x_depth.view(x_depth.shape[0], 1, x_depth.shape[1], x_depth.shape[2]) if x_depth.dim() == 3 else x_depth
+            Cg_H_C, rgb_w, depth_w, mask = _op(ops.warp_rgbd, x_rgb, d4, I_g, I_a, *self._intr,
+                                               _cabi.VIDC_BILINEAR if depth_mode == "bilinear" else _cabi.VIDC_NEAREST)
+            if x_depth.dim() == 3:
+                depth_w = depth_w.view(depth_w.shape[0], depth_w.shape[2], depth_w.shape[3])
+            return Cg_H_C, rgb_w, depth_w, mask
         g, a = _gravity(I_g, I_a, device)
         B = x_rgb.shape[0]
         squeeze = False
