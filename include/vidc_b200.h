@@ -125,6 +125,17 @@ int vidc_rasterize_sparse_depth(const double *d_tracks, const int32_t *d_counts,
                                 double fc0, double fc1, double cc0, double cc1, int32_t H, int32_t W,
                                 int32_t *d_winner_ws, float *d_depth, void *stream);
 
+/* SURVEY.md section 8 row f2, second half: forward warp of RGB plus the SPARSE depth of the frame's KLT tracks without ever
+   building the (mostly zero) depth image: the tracks are rasterised as dataset.py:496-510 does (see above) into an on-chip
+   table and warped analytically; depth_out (B,1,H,W) is bit-identical to vidc_warp_rgbd over vidc_rasterize_sparse_depth's
+   image, for depth_mode bilinear and nearest.  N <= 2048 points per frame; the input must have the canvas size.  Everything
+   else as vidc_warp_rgbd (mask, coverage, d_H_out, workspace). */
+int vidc_warp_rgb_sparse_depth(const vidc_camera *cam, const vidc_image *rgb, const double *d_tracks, const int32_t *d_counts,
+                               int32_t N, int32_t cols, double fc0, double fc1, double cc0, double cc1,
+                               const float *d_Ig, const float *d_Ia, int32_t B_gravity, vidc_interp depth_mode,
+                               vidc_frame_params *d_params_ws, float *d_H_out, const vidc_image *rgb_out,
+                               const vidc_image *depth_out, uint8_t *d_mask_u8, uint32_t *d_coverage, void *stream);
+
 /* Replaces _build_homography (:35-58) plus the per-frame bbox / scale block (:125-140).
    d_Ig, d_Ia: (B,3) contiguous.  d_params: B entries. One thread per frame, no host sync. */
 int vidc_frame_params_compute(const vidc_camera *cam, const float *d_Ig, const float *d_Ia, int32_t B,

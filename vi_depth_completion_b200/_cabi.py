@@ -81,6 +81,9 @@ _SIGNATURES = {
     "vidc_condition_gravity": (ctypes.c_int, [c_f32p, ctypes.c_int32, ctypes.c_int32, c_f32p, c_f32p, ctypes.c_void_p]),
     "vidc_rasterize_sparse_depth": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32] + [ctypes.c_double] * 4 +
                                     [ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, c_f32p, ctypes.c_void_p]),
+    "vidc_warp_rgb_sparse_depth": (ctypes.c_int, [_P(VidcCamera), _P(VidcImage), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32] +
+                                   [ctypes.c_double] * 4 + [c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int, ctypes.c_void_p, c_f32p,
+                                                            _P(VidcImage), _P(VidcImage), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "vidc_debug_div": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, ctypes.c_int64, c_f32p, ctypes.c_void_p]),
 }
 

@@ -162,6 +162,8 @@ __device__ __forceinline__ void warp_rgbd_shear_write_out(const FwdArgs& a, cons
         if (HAS_D)
             *reinterpret_cast<float4*>(a.dep_o + ((long long)b * a.depo_sn + Yo * W + Xo)) =
                 make_float4(px4[0].w, px4[1].w, px4[2].w, px4[3].w);
+        else if (a.dep_o)                                          // sparse-depth path: the plane is zero-filled here, the points
+            *reinterpret_cast<float4*>(a.dep_o + ((long long)b * a.depo_sn + Yo * W + Xo)) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // are warped by warp_sparse_depth_kernel
         if (a.mask || a.coverage) {                                // surface_normal.py:151, four pixels at once
             const unsigned int m0 = (r.x + g.x) + bl.x > 0.01f, m1 = (r.y + g.y) + bl.y > 0.01f;
             const unsigned int m2 = (r.z + g.z) + bl.z > 0.01f, m3 = (r.w + g.w) + bl.w > 0.01f;
@@ -199,7 +201,7 @@ warp_rgbd_shear_kernel(const __grid_constant__ FwdArgs a) {
             *reinterpret_cast<float4*>(o_rgb) = z4;
             *reinterpret_cast<float4*>(o_rgb + W * H) = z4;
             *reinterpret_cast<float4*>(o_rgb + 2 * W * H) = z4;
-            if (HAS_D) *reinterpret_cast<float4*>(a.dep_o + ((long long)b * a.depo_sn + Yo * W + Xo)) = z4;
+            if (HAS_D || a.dep_o) *reinterpret_cast<float4*>(a.dep_o + ((long long)b * a.depo_sn + Yo * W + Xo)) = z4;
             if (a.mask) *reinterpret_cast<unsigned int*>(a.mask + (((long long)b * H + Yo) * W + Xo)) = 0u;
         }
         return;

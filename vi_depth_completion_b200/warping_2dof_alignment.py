@@ -396,6 +396,43 @@ class Warping2DOFAlignment:
         out = (Cg_H_C, rgb_w, depth_w, mask)
         return out + (cov,) if with_coverage else out
 
+    def warp_rgb_sparse_depth(self, x_rgb, tracks, counts, fc, cc, I_g, I_a, depth_mode='bilinear', with_mask=True, with_coverage=False):
+        """warp RGB (B,3,H,W) and the SPARSE depth given as KLT tracks (B,N,>=4) float64 [id, x, y, z, ...] (valid
+        rows per frame in `counts`, loader intrinsics fc, cc: dataset.py:496-510) without building the depth image: the points
+        are rasterised on chip and warped analytically.  Same return tuple and the same bits as
+        warp_rgbd(x_rgb, rasterize_sparse_depth(tracks, counts, fc, cc, H, W), ...)."""
+        _check_interp_mode(depth_mode)
+        _require_cuda_f32(x_rgb, "x_rgb")
+        if not isinstance(tracks, torch.Tensor) or not tracks.is_cuda or tracks.dtype != torch.float64 or tracks.dim() != 3 or tracks.shape[2] < 4:
+            raise RuntimeError("tracks: expected a (B,N,>=4) float64 CUDA tensor")
+        device = x_rgb.device
+        g, a = _gravity(I_g, I_a, device)
+        B = x_rgb.shape[0]
+        tr = tracks.contiguous()
+        if tr.shape[0] != B:
+            raise AssertionError(f"tracks.shape[0]={tr.shape[0]} != x_rgb.shape[0]={B}")
+        cnt = None
+        if counts is not None:
+            cnt = torch.as_tensor(counts, dtype=torch.int32, device=device).contiguous()
+            if cnt.shape != (B,):
+                raise RuntimeError("counts: expected shape (B,)")
+        rgb_w = self._empty_like_canvas(x_rgb)
+        depth_w = torch.empty((B, 1, int(self.H), int(self.W)), dtype=torch.float32, device=device)
+        mask = torch.empty((B, 1, int(self.H), int(self.W)), dtype=torch.uint8, device=device) if with_mask else None
+        cov = torch.empty((B,), dtype=torch.int32, device=device) if with_coverage else None
+        Cg_H_C = torch.empty((g.shape[0], 3, 3), dtype=torch.float32, device=device)
+        ri, rwi, dwi = _image(x_rgb), _image(rgb_w), _image(depth_w)
+        with torch.cuda.device(device):
+            check(lib().vidc_warp_rgb_sparse_depth(ctypes.byref(self._cam), ctypes.byref(ri), tr.data_ptr(), cnt.data_ptr() if cnt is not None else None,
+                                                   tr.shape[1], tr.shape[2], float(fc[0]), float(fc[1]), float(cc[0]), float(cc[1]),
+                                                   g.data_ptr(), a.data_ptr(), g.shape[0],
+                                                   _cabi.VIDC_BILINEAR if depth_mode == "bilinear" else _cabi.VIDC_NEAREST,
+                                                   self._params_ws(g.shape[0], device).data_ptr(), Cg_H_C.data_ptr(), ctypes.byref(rwi),
+                                                   ctypes.byref(dwi), mask.data_ptr() if with_mask else None,
+                                                   cov.data_ptr() if with_coverage else None, _stream_ptr(device)))
+        out = (Cg_H_C, rgb_w, depth_w, mask)
+        return out + (cov,) if with_coverage else out
+
     def warp_rgbd_packed(self, x_rgbd, I_g, I_a, depth_mode='bilinear', with_mask=True, with_coverage=False):
         """Packed RGBD forward warp: x_rgbd is (B,4,h,w) in channels-last memory format (R,G,B,depth interleaved, 16 B per
         pixel), so each bilinear tap is one 128-bit load.  Returns (Cg_H_C, y_rgbd channels-last, mask_u8[, coverage])."""
