@@ -49,3 +49,29 @@ extern "C" void host_exterior_tiles(const vidc_camera* cam, const float* Ig, con
             out[(size_t)i * tiles_x * tiles_y + t] = vidc::tile_certainly_exterior(p, *cam, t % tiles_x, t / tiles_x) ? 1 : 0;
     }
 }
+
+// round 2: the per-frame proof for the inverse warp's shared-reciprocal division, and the per-tile tables of the kernels
+// (prefetch / staging hints) -- the same __host__ __device__ source the per-frame kernels compile
+extern "C" void host_inv_division_proven(const vidc_camera* cam, const float* Ig, const float* Ia, int B, unsigned char* out,
+                                         vidc_frame_params* params_out) {
+    for (int i = 0; i < B; ++i) {
+        vidc_frame_params p;
+        memset(&p, 0, sizeof p);
+        vidc::frame_params_from_gravity(*cam, Ig + 3 * i, Ia + 3 * i, p);
+        out[i] = vidc::inv_division_proven(p, *cam) ? 1 : 0;
+        if (params_out) params_out[i] = p;
+    }
+}
+extern "C" void host_tile_tables(const vidc_camera* cam, const float* Ig, const float* Ia, int B, uint32_t* inv_boxes, uint32_t* fwd_boxes) {
+    const int tiles_x = (cam->W + 31) / 32, tiles_y = (cam->H + 31) / 32, nt = tiles_x * tiles_y;
+    for (int i = 0; i < B; ++i) {
+        vidc_frame_params p;
+        memset(&p, 0, sizeof p);
+        vidc::frame_params_from_gravity(*cam, Ig + 3 * i, Ia + 3 * i, p);
+        const bool proven = vidc::inv_division_proven(p, *cam);
+        for (int t = 0; t < nt; ++t) {
+            vidc::inv_tile_boxes(p, *cam, t % tiles_x, t / tiles_x, proven, inv_boxes + ((size_t)i * nt + t) * 4);
+            vidc::fwd_tile_src_box(p, *cam, t % tiles_x, t / tiles_x, fwd_boxes + ((size_t)i * nt + t) * 4);
+        }
+    }
+}

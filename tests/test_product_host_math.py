@@ -138,3 +138,107 @@ def test_exterior_tile_test_is_conservative(hlib, oracle_mod, cam_name):
     print(f"{cam_name}: {marked} of {truly} exterior tiles marked")
     if cam_name != "tiny":                # on the 2 x 2 tiles of the tiny canvas few tiles are exterior at all
         assert marked > 0.6 * truly > 0
+
+
+# ---- round 2: the division proof and the per-tile tables (csrc/frame_params.cuh) on the CPU ---------------------------------
+def _f32_fma(a, b, c):
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)   # exact product, one rounding
+
+
+def test_inverse_division_proof_holds_for_every_pixel(hlib):
+    """vidc::inv_division_proven lets the inverse kernels drop their per-pixel window test.  For every frame it accepts, the
+    kernels' own fp32 u, v, s (fma(H1, Y, H0 X) + H2) must lie inside the window the shared-reciprocal division is exact in --
+    |s| in [2^-40, 2^40], numerators zero or in [2^-80, 2^80] -- at EVERY pixel; frames whose horizon crosses the image, and
+    degenerate gravity, must be rejected or pass the same check."""
+    cams = ["S1", "S2", "tiny"]
+    f = np.float32
+    n_proven = 0
+    for name in cams:
+        g1, a1 = C.random_gravity(24, seed=5, roll_deg=90, pitch_deg=85)
+        g2, a2 = C.edge_case_gravity()
+        g3, a3 = C.degenerate_gravity()
+        g4, a4 = C.isolated_nonfinite_gravity()
+        I_g, I_a = np.concatenate([g1, g2, g3, g4]), np.concatenate([a1, a2, a3, a4])
+        B = I_g.shape[0]
+        from vi_depth_completion_b200._cabi import VidcCamera, lib
+        c = VidcCamera()
+        assert lib().vidc_camera_init(*[float(v) for v in C.CAMERAS[name]], ctypes.byref(c)) == 0
+        flags = np.zeros(B, np.uint8); prm = np.zeros((B, 48), np.float32)
+        hlib.host_inv_division_proven(ctypes.byref(c), _p(np.ascontiguousarray(I_g)), _p(np.ascontiguousarray(I_a)), B, _p(flags), _p(prm))
+        X, Y = np.meshgrid(np.arange(c.W, dtype=f), np.arange(c.H, dtype=f))
+        with np.errstate(all="ignore"):
+            for b in range(B):
+                Hm = prm[b, :9]
+                s = _f32_fma(np.full_like(X, Hm[7]), Y, Hm[6] * X) + Hm[8]
+                u = _f32_fma(np.full_like(X, Hm[1]), Y, Hm[0] * X) + Hm[2]
+                v = _f32_fma(np.full_like(X, Hm[4]), Y, Hm[3] * X) + Hm[5]
+                ok_s = (np.abs(s) >= 2.0 ** -40) & (np.abs(s) <= 2.0 ** 40)
+                ok_n = ((u == 0) | ((np.abs(u) >= 2.0 ** -80) & (np.abs(u) <= 2.0 ** 80))) & ((v == 0) | ((np.abs(v) >= 2.0 ** -80) & (np.abs(v) <= 2.0 ** 80)))
+                if flags[b]:
+                    n_proven += 1
+                    assert bool(ok_s.all() and ok_n.all()), f"{name} frame {b}: accepted by the proof but a pixel leaves the window"
+    assert n_proven >= 60                                           # the proof is not vacuous: ordinary frames pass it
+    # and every frame of the bench workload passes (the kernels run without the window test there)
+    I_g, I_a = C.random_gravity(256, seed=1234, roll_deg=30, pitch_deg=30)
+    c = VidcCamera()
+    lib().vidc_camera_init(*[float(v) for v in C.CAMERAS["S2"]], ctypes.byref(c))
+    flags = np.zeros(256, np.uint8)
+    hlib.host_inv_division_proven(ctypes.byref(c), _p(I_g), _p(I_a), 256, _p(flags), None)
+    assert flags.all()
+
+
+def test_tile_tables_cover_the_footprints(hlib, oracle_mod):
+    """The per-tile tables are hints (no result depends on them) but a useless hint would cost the speed they exist for:
+    the staged-inverse boxes must contain the taps of (nearly) every pixel of their tile, the forward source boxes must
+    contain every in-image tap of their tile -- checked against the oracle's sampling grids on the S2 workload."""
+    from vi_depth_completion_b200._cabi import VidcCamera, lib
+    cam = C.CAMERAS["S2"]
+    c = VidcCamera()
+    lib().vidc_camera_init(*[float(v) for v in cam], ctypes.byref(c))
+    B = 6
+    I_g, I_a = C.random_gravity(B, seed=1234, roll_deg=30, pitch_deg=30)
+    tx, ty = (c.W + 31) // 32, (c.H + 31) // 32
+    inv = np.zeros((B, ty, tx, 4), np.uint32); fwd = np.zeros((B, ty, tx, 4), np.uint32)
+    hlib.host_tile_tables(ctypes.byref(c), _p(I_g), _p(I_a), B, _p(inv), _p(fwd))
+    orc = oracle_mod.Oracle(*cam)
+    _, grid, igrid = orc.image_sampler_forward_inverse(I_g, I_a)
+    W, H = c.W, c.H
+
+    def taps(gr):
+        ix = ((gr[..., 0] + 1) * W - 1) / 2; iy = ((gr[..., 1] + 1) * H - 1) / 2
+        return np.floor(ix).astype(np.int64), np.floor(iy).astype(np.int64)
+
+    x0, y0 = taps(igrid)
+    inside = total = 0
+    for b in range(B):
+        for j in range(ty):
+            for i in range(tx):
+                e = inv[b, j, i]
+                nsub = (int(e[1]) >> 16) & 3
+                xs = x0[b, j * 32:(j + 1) * 32, i * 32:(i + 1) * 32]; ys = y0[b, j * 32:(j + 1) * 32, i * 32:(i + 1) * 32]
+                total += xs.size
+                if nsub == 0:
+                    continue
+                for sub in range(nsub):
+                    w0, w1 = int(e[2 * sub]), int(e[2 * sub + 1])
+                    bx0 = ((w0 & 0xffff) ^ 0x8000) - 0x8000; by0 = (w0 >> 16) - (0x10000 if w0 >> 31 else 0)
+                    bw, bh = w1 & 0xff, (w1 >> 8) & 0xff
+                    rows = slice(0, 32) if nsub == 1 else slice(16 * sub, 16 * sub + 16)
+                    ax, ay = xs[rows] - bx0, ys[rows] - by0
+                    inside += int(((ax >= 0) & (ax < bw - 1) & (ay >= 0) & (ay < bh - 1)).sum())
+                    assert bx0 % 4 == 0 and bw <= 60 and bh <= 40
+    assert inside / total > 0.995, inside / total
+    x0, y0 = taps(grid)
+    missed = seen = 0
+    for b in range(B):
+        for j in range(ty):
+            for i in range(tx):
+                bx, by, bw, bh = [int(v) for v in fwd[b, j, i]]
+                xs = x0[b, j * 32:(j + 1) * 32, i * 32:(i + 1) * 32]; ys = y0[b, j * 32:(j + 1) * 32, i * 32:(i + 1) * 32]
+                live = (xs >= 0) & (xs < W - 1) & (ys >= 0) & (ys < H - 1)
+                seen += int(live.sum())
+                if bw == 0:
+                    missed += int(live.sum())
+                    continue
+                missed += int((live & ~((xs >= bx) & (xs + 1 < bx + bw) & (ys >= by) & (ys + 1 < by + bh))).sum())
+    assert missed / seen < 0.002, missed / seen
