@@ -518,6 +518,36 @@ def run_ours(args):
             cpu_port["reference_error"] = repr(e)[:300]
         if cpu is None:
             cpu, cpu_port = cpu_port, None
+    # ---- e2e with the RGB frames as the DataLoader holds them before to_tensor: (B,H,W,3) uint8 (secondary; N == 1) ----------
+    e2e_u8 = None
+    if rank == 0 and world == 1:
+        try:
+            gen = torch.Generator().manual_seed(77)
+            h_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=gen).pin_memory()
+
+            def e2e_u8_step():
+                _cabi.check(lib.vidc_warp_unwarp_host_u8(ctypes.byref(w._cam), B, h_u8.data_ptr(), h_depth.data_ptr(), h_nrm.data_ptr(),
+                                                         h_g.data_ptr(), h_a.data_ptr(), o_rgb.data_ptr(), o_depth.data_ptr(),
+                                                         o_mask.data_ptr(), o_nrm.data_ptr(), ctypes.c_void_p(stream)))
+            for _ in range(2):
+                e2e_u8_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(Ke):
+                e2e_u8_step()
+            torch.cuda.synchronize()
+            u8_s = time.perf_counter() - t0
+            # same bits as the resident float path on ToTensor(frames), checked on the first 8 frames
+            x8 = h_u8[:8].permute(0, 3, 1, 2).to(torch.float32).div(255).contiguous().to(dev)
+            _, rw8, _, mk8 = w.warp_rgbd(x8, depth[:8], g[:8], a[:8])
+            torch.cuda.synchronize()
+            e2e_u8 = {"value": B * Ke / u8_s, "unit": UNIT, "h2d_bytes_per_step": h2d - h_rgb.numel() * 4 + h_u8.numel(),
+                      "d2h_bytes_per_step": d2h, "steps": Ke,
+                      "api": "vidc_warp_unwarp_host_u8 (RGB as (B,H,W,3) uint8 host buffers, ToTensor on the device inside the pipeline)",
+                      "matches_resident_path_on_to_tensor": bool(torch.equal(rw8.cpu(), o_rgb[:8]) and torch.equal(mk8.cpu(), o_mask[:8]))}
+            del h_u8, x8, rw8, mk8
+        except Exception as e:                                    # a secondary number must never take the bench down
+            e2e_u8 = {"error": repr(e)[:300]}
     del h_rgb, h_depth, h_nrm, o_rgb, o_depth, o_mask, o_nrm
 
     # ---- config 5: the reference's CNNs (random init) around the warp, before / after; every rank takes part -------------------
@@ -581,6 +611,7 @@ def run_ours(args):
             "config5": c5,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "api": "vidc_warp_unwarp_host (C ABI, pinned host buffers)", "matches_resident_path": e2e_ok},
+            "e2e_u8": e2e_u8,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

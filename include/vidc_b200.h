@@ -253,6 +253,20 @@ int vidc_warp_unwarp_host(const vidc_camera *cam, int32_t B,
                           void *stream);
 int vidc_release_workspace(void);
 
+/* ---- the data format on the DataLoader side of the path (dataset.py:468-471) ----------------
+   torchvision's ToTensor on device: (B,H,W,C) uint8 as PIL decodes it -> (B,C,H,W) float32 = x / 255, the correctly rounded
+   fp32 quotient ToTensor's .div(255) produces (bit-identical); C in 1..4.  15 B/px of HBM traffic for RGB. */
+int vidc_to_tensor_u8(const uint8_t *d_hwc, int32_t B, int32_t H, int32_t W, int32_t C, float *d_chw, void *stream);
+
+/* vidc_warp_unwarp_host with the RGB frames as (B,H,W,3) uint8 HOST buffers (what the reference's loader holds before
+   to_tensor): a quarter of the RGB bytes cross PCIe and vidc_to_tensor_u8 runs on the device inside the pipeline.  Outputs
+   are bit-identical to vidc_warp_unwarp_host on ToTensor(h_rgb_u8). */
+int vidc_warp_unwarp_host_u8(const vidc_camera *cam, int32_t B,
+                             const uint8_t *h_rgb_u8, const float *h_depth, const float *h_normals,
+                             const float *h_Ig, const float *h_Ia,
+                             float *h_rgb_w, float *h_depth_w, uint8_t *h_mask, float *h_normals_cam,
+                             void *stream);
+
 /* Test hook: runs the kernels' shared-reciprocal division helpers next to the compiler's IEEE
    division on n device operand triples (u, v, s); d_out receives 4*n floats
    [u/s fast | v/s fast | u/s IEEE | v/s IEEE].  Used by tests/test_gpu_math.py only. */

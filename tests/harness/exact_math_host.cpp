@@ -75,3 +75,8 @@ extern "C" void host_tile_tables(const vidc_camera* cam, const float* Ig, const 
         }
     }
 }
+
+// ToTensor's x / 255 as the device kernels evaluate it (csrc/frame_params.cuh: u8_to_unit)
+extern "C" void host_u8_to_unit(const unsigned char* in, int n, float* out) {
+    for (int i = 0; i < n; ++i) out[i] = vidc::u8_to_unit(in[i]);
+}

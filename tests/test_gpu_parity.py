@@ -232,6 +232,22 @@ def test_errors(cuda_device):
     _, y = w.unwarp_normals(x, g, g)                        # fused renormalising entry point: forward-only
     with pytest.raises(NotImplementedError):
         y.sum().backward()
+    # the same for the fused forward entry (through the torch extension and through ctypes): never a silent zero gradient
+    import warnings
+    for kw in ({}, {"with_coverage": True}):
+        x = torch.rand(2, 3, 240, 320, device=cuda_device, requires_grad=True)
+        out = w.warp_rgbd(x, torch.rand(2, 240, 320, device=cuda_device), g, g, **kw)
+        assert out[1].requires_grad
+        with warnings.catch_warnings():
+            warnings.simplefilter("error")                              # torch's "autograd kernel was not registered" warning included
+            with pytest.raises(NotImplementedError):
+                out[1].sum().backward()
+    x = torch.rand(2, 3, 240, 320, device=cuda_device, requires_grad=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        _, y = w.warp_with_gravity_center_aligned(x, g, g)
+        y.sum().backward()                                              # differentiable method: no fallback node in the graph
+    assert x.grad is not None and torch.isfinite(x.grad).all()
 
 
 def test_empty_batch(cuda_device):

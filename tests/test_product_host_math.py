@@ -242,3 +242,19 @@ def test_tile_tables_cover_the_footprints(hlib, oracle_mod):
                     continue
                 missed += int((live & ~((xs >= bx) & (xs + 1 < bx + bw) & (ys >= by) & (ys + 1 < by + bh))).sum())
     assert missed / seen < 0.002, missed / seen
+
+
+def test_u8_to_unit_is_to_tensor(hlib):
+    """vidc::u8_to_unit (the ToTensor kernels' x / 255, three fp32 operations) against torch's .div(255) and torchvision's
+    ToTensor on a PIL image (dataset.py:468-471) for every uint8 value: bit-identical."""
+    import torch
+    from PIL import Image
+    from torchvision import transforms
+    vals = np.arange(256, dtype=np.uint8)
+    out = np.empty(256, np.float32)
+    hlib.host_u8_to_unit(vals.ctypes.data_as(ctypes.c_void_p), 256, out.ctypes.data_as(ctypes.c_void_p))
+    want = torch.from_numpy(vals).to(torch.float32).div(255).numpy()
+    assert C.count_bit_mismatches(out, want) == 0
+    img = np.stack([vals.reshape(16, 16)] * 3, -1)                                   # (16,16,3) uint8, every value once per channel
+    tv = transforms.ToTensor()(Image.fromarray(img)).numpy()
+    assert C.count_bit_mismatches(tv[0].reshape(-1), out) == 0

@@ -78,6 +78,8 @@ _SIGNATURES = {
                                                  _P(VidcImage), ctypes.c_void_p]),
     "vidc_warp_unwarp_host": (ctypes.c_int, [_P(VidcCamera), ctypes.c_int32] + [ctypes.c_void_p] * 10),
     "vidc_release_workspace": (ctypes.c_int, []),
+    "vidc_to_tensor_u8": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int32] * 4 + [c_f32p, ctypes.c_void_p]),
+    "vidc_warp_unwarp_host_u8": (ctypes.c_int, [_P(VidcCamera), ctypes.c_int32] + [ctypes.c_void_p] * 10),
     "vidc_condition_gravity": (ctypes.c_int, [c_f32p, ctypes.c_int32, ctypes.c_int32, c_f32p, c_f32p, ctypes.c_void_p]),
     "vidc_rasterize_sparse_depth": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32] + [ctypes.c_double] * 4 +
                                     [ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, c_f32p, ctypes.c_void_p]),

@@ -223,6 +223,16 @@ VIDC_HD InvBox inv_rect_box(const vidc_frame_params& p, const vidc_camera& cam, 
     return b;
 }
 
+// torchvision's ToTensor on a uint8 image (dataset.py:468-471: PIL image -> to_tensor): img.to(float32).div(255), one correctly
+// rounded fp32 division per value.  q = x c with c = fl(1 / 255), r = x - 255 q (exact in one FMA), q + r c: the correctly
+// rounded quotient for every x in 0..255 (all 256 values are compared with torch in tests/test_product_host_math.py).
+VIDC_HD float u8_to_unit(unsigned int p) {
+    const float x = (float)p, c = 0.003921568859368563f;
+    const float q = x * c;
+    const float r = fmaf(-q, 255.0f, x);
+    return fmaf(r, c, q);
+}
+
 // The shared-reciprocal division of the hot kernels (kernels_fast.cuh: div2_rn) is the correctly rounded quotient while
 // |s| lies in [2^-40, 2^40] and each numerator is zero or lies in [2^-80, 2^80].  For the inverse warp u, v, s are
 // fma(H1, Y, H0 X) + H2 with integer pixel coordinates 0 <= X, Y < 2^15, so a non-zero numerator is a multiple of the

@@ -402,4 +402,30 @@ normal_loss_backward_kernel(ImgView gt, ImgView pred, ImgView mask, int mode, co
     for (int c = 3; c < gp.c; ++c) po[c * gp.sc] = 0.0f;
 }
 
+// ---- ToTensor on device (dataset.py:468-471, the data format on the DataLoader side of the path) -----------------------------
+// (B,H,W,C) uint8 as PIL decodes it -> (B,C,H,W) float = x / 255.  HBM-bound: C bytes in, 4 C bytes out per pixel.
+// RGB fast path: thread -> 4 consecutive pixels = three aligned 32-bit loads, one 128-bit store per plane.
+__global__ void __launch_bounds__(256) to_tensor_rgb_u8_kernel(const uint32_t* __restrict__ in, long long hw, float* __restrict__ out) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;            // quad of pixels inside the frame
+    if (4 * q >= hw) return;
+    const int b = blockIdx.y;
+    const uint32_t* __restrict__ src = in + ((long long)b * hw * 3) / 4 + 3 * q;
+    const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);        // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+    float* __restrict__ o = out + (long long)b * 3 * hw + 4 * q;
+    *reinterpret_cast<float4*>(o) = make_float4(vidc::u8_to_unit(w0 & 255u), vidc::u8_to_unit(w0 >> 24),
+                                                vidc::u8_to_unit((w1 >> 16) & 255u), vidc::u8_to_unit((w2 >> 8) & 255u));
+    *reinterpret_cast<float4*>(o + hw) = make_float4(vidc::u8_to_unit((w0 >> 8) & 255u), vidc::u8_to_unit(w1 & 255u),
+                                                     vidc::u8_to_unit(w1 >> 24), vidc::u8_to_unit((w2 >> 16) & 255u));
+    *reinterpret_cast<float4*>(o + 2 * hw) = make_float4(vidc::u8_to_unit((w0 >> 16) & 255u), vidc::u8_to_unit((w1 >> 8) & 255u),
+                                                         vidc::u8_to_unit(w2 & 255u), vidc::u8_to_unit(w2 >> 24));
+}
+// any channel count / size: thread -> one output value
+__global__ void __launch_bounds__(256) to_tensor_u8_kernel(const uint8_t* __restrict__ in, long long hw, int C, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;            // pixel inside the frame
+    if (i >= hw) return;
+    const int b = blockIdx.y;
+    const uint8_t* __restrict__ src = in + ((long long)b * hw + i) * C;
+    for (int c = 0; c < C; ++c) out[((long long)b * C + c) * hw + i] = vidc::u8_to_unit(src[c]);
+}
+
 }  // namespace vidc_k

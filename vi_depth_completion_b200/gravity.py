@@ -47,3 +47,23 @@ def rasterize_sparse_depth(tracks: torch.Tensor, counts, fc, cc, H: int, W: int)
                                                 float(fc[0]), float(fc[1]), float(cc[0]), float(cc[1]), H, W,
                                                 ws.data_ptr(), depth.data_ptr(), _stream_ptr(tr.device)))
     return depth
+
+
+def to_tensor_u8(images: torch.Tensor):
+    """torchvision's ToTensor on the device (dataset.py:468-471): (B,H,W,C) or (H,W,C) uint8 CUDA, the layout PIL decodes to
+    -> (B,C,H,W) / (C,H,W) float32 = x / 255, bit-identical to `transforms.ToTensor()` (one correctly rounded division)."""
+    if not images.is_cuda or images.dtype != torch.uint8 or images.dim() not in (3, 4):
+        raise RuntimeError("images: expected a (B,H,W,C) or (H,W,C) uint8 CUDA tensor")
+    x = images.contiguous()
+    single = x.dim() == 3
+    if single:
+        x = x.unsqueeze(0)
+    B, H, W, C = x.shape
+    if not 1 <= C <= 4:
+        raise RuntimeError(f"images: 1..4 channels, got {C}")
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        for b0 in range(0, B, 65535):
+            n = min(65535, B - b0)
+            check(lib().vidc_to_tensor_u8(x[b0:b0 + n].data_ptr(), n, H, W, C, out[b0:b0 + n].data_ptr(), _stream_ptr(x.device)))
+    return out[0] if single else out

@@ -248,7 +248,9 @@ class Warping2DOFAlignment:
         ops = _torchops.ops()
         needs_graph = torch.is_grad_enabled() and x.requires_grad
         if ops is not None and isinstance(I_g, torch.Tensor) and isinstance(I_a, torch.Tensor):
-            Cg_H_C, y = _op(ops.warp_forward, x, I_g, I_a, *self._intr, mode)          # thin torch C++ extension
+            # thin torch C++ extension; the operators carry no autograd kernel -- the graph is attached below (_attach), so they
+            # only ever see detached tensors (torch's not-implemented fallback would otherwise hand out silent zero gradients)
+            Cg_H_C, y = _op(ops.warp_forward, x.detach() if needs_graph else x, I_g, I_a, *self._intr, mode)
             g, a = _gravity(I_g, I_a, device) if needs_graph else (None, None)
         else:
             g, a = _gravity(I_g, I_a, device)
@@ -292,8 +294,9 @@ class Warping2DOFAlignment:
         device = x.device
         ops = _torchops.ops()
         if ops is not None and not want_valid and isinstance(I_g, torch.Tensor) and isinstance(I_a, torch.Tensor):
-            Cg_H_C, z = _op(ops.unwarp_normals, x, I_g, I_a, *self._intr, bool(normalize))   # thin torch C++ extension
-            if torch.is_grad_enabled() and x.requires_grad:
+            needs_graph = torch.is_grad_enabled() and x.requires_grad
+            Cg_H_C, z = _op(ops.unwarp_normals, x.detach() if needs_graph else x, I_g, I_a, *self._intr, bool(normalize))
+            if needs_graph:
                 g, a = _gravity(I_g, I_a, device)
                 z = _attach(x, z, self, g, a, True, _cabi.VIDC_BILINEAR) if not normalize else _attach(x, z)
             return Cg_H_C, z, None
@@ -361,11 +364,12 @@ class Warping2DOFAlignment:
         if (ops is not None and with_mask and not with_coverage and isinstance(x_depth, torch.Tensor) and x_rgb.dim() == 4
                 and isinstance(I_g, torch.Tensor) and isinstance(I_a, torch.Tensor)):
             d4 = x_depth.view(x_depth.shape[0], 1, x_depth.shape[1], x_depth.shape[2]) if x_depth.dim() == 3 else x_depth
-            Cg_H_C, rgb_w, depth_w, mask = _op(ops.warp_rgbd, x_rgb, d4, I_g, I_a, *self._intr,
+            Cg_H_C, rgb_w, depth_w, mask = _op(ops.warp_rgbd, x_rgb.detach() if x_rgb.requires_grad else x_rgb,
+                                               d4.detach() if d4.requires_grad else d4, I_g, I_a, *self._intr,
                                                _cabi.VIDC_BILINEAR if depth_mode == "bilinear" else _cabi.VIDC_NEAREST)
             if x_depth.dim() == 3:
                 depth_w = depth_w.view(depth_w.shape[0], depth_w.shape[2], depth_w.shape[3])
-            return Cg_H_C, rgb_w, depth_w, mask
+            return Cg_H_C, _attach(x_rgb, rgb_w), _attach(x_depth, depth_w), mask          # forward-only: backward raises
         g, a = _gravity(I_g, I_a, device)
         B = x_rgb.shape[0]
         squeeze = False
@@ -393,7 +397,7 @@ class Warping2DOFAlignment:
                                        _stream_ptr(device)))
         if squeeze:
             depth_w = depth_w.view(B, depth_w.shape[2], depth_w.shape[3])
-        out = (Cg_H_C, rgb_w, depth_w, mask)
+        out = (Cg_H_C, _attach(x_rgb, rgb_w), depth_w if depth_w is None else _attach(x_depth, depth_w), mask)   # forward-only
         return out + (cov,) if with_coverage else out
 
     def warp_rgb_sparse_depth(self, x_rgb, tracks, counts, fc, cc, I_g, I_a, depth_mode='bilinear', with_mask=True, with_coverage=False):
@@ -430,7 +434,7 @@ class Warping2DOFAlignment:
                                                    self._params_ws(g.shape[0], device).data_ptr(), Cg_H_C.data_ptr(), ctypes.byref(rwi),
                                                    ctypes.byref(dwi), mask.data_ptr() if with_mask else None,
                                                    cov.data_ptr() if with_coverage else None, _stream_ptr(device)))
-        out = (Cg_H_C, rgb_w, depth_w, mask)
+        out = (Cg_H_C, _attach(x_rgb, rgb_w), depth_w, mask)                       # forward-only
         return out + (cov,) if with_coverage else out
 
     def warp_rgbd_packed(self, x_rgbd, I_g, I_a, depth_mode='bilinear', with_mask=True, with_coverage=False):
@@ -453,7 +457,7 @@ class Warping2DOFAlignment:
                                               self._params_ws(g.shape[0], device).data_ptr(), Cg_H_C.data_ptr(), y.data_ptr(),
                                               mask.data_ptr() if with_mask else None, cov.data_ptr() if with_coverage else None,
                                               _stream_ptr(device)))
-        out = (Cg_H_C, y, mask)
+        out = (Cg_H_C, _attach(x_rgbd, y), mask)                                   # forward-only
         return out + (cov,) if with_coverage else out
 
     def unwarp_normals(self, y, I_g, I_a, normalize=True, with_valid=False):
