@@ -113,6 +113,7 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor> warp_rgbd(const at::T
     check_f32_cuda(rgb, "x_rgb");
     check_f32_cuda(depth, "x_depth");
     TORCH_CHECK(rgb.dim() == 4 && depth.dim() == 4, "warp_rgbd: expected (B,3,h,w) and (B,1,h,w)");
+    TORCH_CHECK(depth.device() == rgb.device(), "x_depth must live on ", rgb.device(), ", got ", depth.device());
     const vidc_camera cam = make_camera(fx, fy, cx, cy);
     const c10::cuda::CUDAGuard guard(rgb.device());
     auto [g, a] = gravity(I_g, I_a, rgb.device());

@@ -377,6 +377,8 @@ class Warping2DOFAlignment:
         depth_w = None
         if x_depth is not None:
             _require_cuda_f32(x_depth, "x_depth")
+            if x_depth.device != device:
+                raise RuntimeError(f"x_depth must live on {device}, got {x_depth.device}")
             if x_depth.dim() == 3:
                 x_depth = x_depth.view(x_depth.shape[0], 1, x_depth.shape[1], x_depth.shape[2])
                 squeeze = True
