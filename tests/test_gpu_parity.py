@@ -312,12 +312,13 @@ print("VARIANT_OK")
 
 
 @pytest.mark.parametrize("env", [{"VIDC_SHEAR": "0"}, {"VIDC_SHEAR": "1"}, {"VIDC_SHEAR": "2"}, {"VIDC_TMA": "1"},
-                                 {"VIDC_TILE_SKIP": "0"}, {"VIDC_INV_BOX": "1"}],
-                         ids=["straight-rows", "sheared-forward", "sheared-both", "tma-staged", "no-tile-skip", "inverse-box-staged"])
+                                 {"VIDC_TILE_SKIP": "0"}, {"VIDC_INV_BOX": "1"}, {"VIDC_TMA_STORE": "0"}],
+                         ids=["straight-rows", "sheared-forward", "sheared-both", "tma-staged", "no-tile-skip", "inverse-box-staged", "lsu-write-out"])
 def test_kernel_variants_match_oracle(cuda_device, oracle_mod, env):
     """Every kernel family behind the fused entry points, each selected by its environment switch in a fresh process:
     straight row segments (VIDC_SHEAR=0), sheared forward rows only (=1), sheared forward + inverse (=2, the default) and
-    the opt-in TMA-staged kernels (VIDC_TMA=1).  Same bits as the oracle for moderate, extreme (column-major tiles) and
+    the opt-in TMA-staged kernels (VIDC_TMA=1); VIDC_TMA_STORE=0 replaces the default TMA write-out of the sheared kernels (bulk
+    tensor stores from a planar staging tile) by their LSU write-out.  Same bits as the oracle for moderate, extreme (column-major tiles) and
     edge-case gravity, both depth modes, coverage counts, RGB-only calls, a canvas whose height is not a multiple of
     the tile (240) and the special-value images."""
     import os

@@ -52,6 +52,24 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 }
 
 
+// ---- tiled bulk tensor STORES (shared -> global, SASS UTMASTG): the write-out of the sheared kernels ----------------------
+// Elements of the box that fall outside the tensor are not written.  Every thread that wrote the staged tile through the
+// generic proxy fences (fence_async_smem) before the barrier; one thread then issues the stores, commits the group and waits
+// until the TMA unit has READ the tile (the CTA must not exit -- and hand its shared memory to the next CTA -- earlier).
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int x, int y, int c, int n) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"((unsigned long long)map), "r"(smem_u32(smem_src)), "r"(x), "r"(y), "r"(c), "r"(n) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int x, int y, int n) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"((unsigned long long)map), "r"(smem_u32(smem_src)), "r"(x), "r"(y), "r"(n) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // plain arrive (no transaction bytes) and arrive from a consumer warp
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
