@@ -160,6 +160,42 @@ def test_channels_last_input_no_copy(cuda_device, oracle_mod):
     assert C.count_bit_mismatches(z.cpu().numpy(), oz) == 0
 
 
+def test_outputs_a_tensor_map_cannot_describe(cuda_device, oracle_mod):
+    """The TMA write-out needs 16-byte aligned outputs (and mask): a caller of the C ABI that hands over anything else gets the
+    LSU write-out of the same kernels -- same bits, no error.  Outputs placed 4 / 8 bytes into their allocations."""
+    import ctypes
+    from vi_depth_completion_b200 import _cabi
+    from vi_depth_completion_b200.warping_2dof_alignment import _image
+    w, o = _mk("S1", cuda_device)
+    B, Hh, Ww = 3, int(w.H), int(w.W)
+    I_g, I_a = C.random_gravity(B, seed=77)
+    rgb, depth, normals = C.random_images(B, Hh, Ww, seed=14)
+    g, a = _t(I_g, cuda_device), _t(I_a, cuda_device)
+    x, d, n = _t(rgb, cuda_device), _t(depth, cuda_device)[:, None].contiguous(), _t(normals, cuda_device)
+    _, oy = o.warp_with_gravity_center_aligned(rgb, I_g, I_a)
+    _, od = o.warp_with_gravity_center_aligned(depth, I_g, I_a)
+    _, oz = o.inverse_warp_normal_image_with_gravity_center_aligned(normals, I_g, I_a)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(cuda_device).cuda_stream)
+    ws = w._params_ws(B, cuda_device)
+    for off_f, off_m in ((1, 0), (2, 4), (0, 4), (0, 8)):                       # floats into the fp32 outputs, bytes into the mask
+        buf_rgb = torch.zeros(B * 3 * Hh * Ww + 4, device=cuda_device); buf_dep = torch.zeros(B * Hh * Ww + 4, device=cuda_device)
+        buf_z = torch.zeros(B * 3 * Hh * Ww + 4, device=cuda_device); buf_m = torch.zeros(B * Hh * Ww + 16, dtype=torch.uint8, device=cuda_device)
+        y = buf_rgb[off_f:off_f + B * 3 * Hh * Ww].view(B, 3, Hh, Ww); yd = buf_dep[off_f:off_f + B * Hh * Ww].view(B, 1, Hh, Ww)
+        z = buf_z[off_f:off_f + B * 3 * Hh * Ww].view(B, 3, Hh, Ww); m = buf_m[off_m:off_m + B * Hh * Ww].view(B, 1, Hh, Ww)
+        xi, di, yi, ydi, ni, zi = _image(x), _image(d), _image(y), _image(yd), _image(n), _image(z)
+        with torch.cuda.device(cuda_device):
+            _cabi.check(_cabi.lib().vidc_warp_rgbd(ctypes.byref(w._cam), ctypes.byref(xi), ctypes.byref(di), g.data_ptr(), a.data_ptr(), B,
+                                                   _cabi.VIDC_BILINEAR, ws.data_ptr(), None, ctypes.byref(yi), ctypes.byref(ydi),
+                                                   m.data_ptr(), None, stream))
+            _cabi.check(_cabi.lib().vidc_unwarp_normals(ctypes.byref(w._cam), ctypes.byref(ni), g.data_ptr(), a.data_ptr(), B, 0,
+                                                        ws.data_ptr(), None, ctypes.byref(zi), None, stream))
+        assert C.count_bit_mismatches(y.cpu().numpy(), oy) == 0, (off_f, off_m)
+        assert C.count_bit_mismatches(yd.cpu().numpy()[:, 0], od) == 0, (off_f, off_m)
+        assert np.array_equal(m.cpu().numpy(), oracle_mod.validity_mask(oy)), (off_f, off_m)
+        assert C.count_bit_mismatches(z.cpu().numpy(), oz) == 0, (off_f, off_m)
+        assert buf_m[:off_m].sum().item() == 0 and buf_m[off_m + B * Hh * Ww:].sum().item() == 0       # nothing written outside
+
+
 def test_coverage_counts(cuda_device, oracle_mod):
     w, o = _mk("S1", cuda_device)
     I_g, I_a = C.random_gravity(5, seed=31)

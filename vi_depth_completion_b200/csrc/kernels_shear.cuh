@@ -13,9 +13,12 @@
 // ANY roll (the straight-row kernels need a separate column-major tile path near +-90 deg and lose 20-40 % between
 // 30 and 75 deg).  Every pixel of the tile is still produced exactly once -- 8 warps x 4 segments cover each column's
 // (row's) 32 pixels -- by exactly the same arithmetic: only the lane -> pixel assignment changes, so the bits do not.
-// The results are staged in a 32x32 pixel-interleaved shared tile (one 128-bit deposit per pixel, XOR-swizzled so that
-// deposits and read-out are bank-conflict-free in both orientations) and leave as 128-bit row stores per plane; the
-// validity mask and the coverage count are computed from the staged values.
+// The results are staged in shared memory and leave in one of two ways (chosen per CTA, same bits):
+//   * TMA write-out (default, lanes along X): planar (plane, row, column) tile, bulk tensor stores issued by one thread
+//     (StoreMaps below);
+//   * LSU write-out (lanes along Y, validity output, VIDC_TMA_STORE=0): a 32x32 pixel-interleaved tile (one 128-bit deposit
+//     per pixel, XOR-swizzled so that deposits and read-out are bank-conflict-free in both orientations), 128-bit row stores
+//     per plane, validity mask and coverage count from the staged values.
 //
 // Without running output pointers the hot paths fit 32 registers: 8 CTAs = 64 warps are resident per SM where the
 // straight-row kernels run 5 CTAs at 48 registers, which hides more of the gather latency than the smaller L1
