@@ -385,9 +385,10 @@ def run_ours(args):
 
     lib = _cabi.lib()
 
-    def step():
-        w.warp_rgbd(rgb, depth, g, a)          # params + fused forward (RGB, depth, mask)
-        w.unwarp_normals(normals, g, a)        # params + fused inverse (gather, R^T, normalise)
+    def step():                                # params kernel + forward kernel + inverse kernel
+        p = w.prepare(g, a)               # per-frame parameters, once for the batch
+        w.warp_rgbd(rgb, depth, params=p)      # fused forward (RGB, depth, mask)
+        w.unwarp_normals(normals, params=p)    # fused inverse (gather, R^T, normalise)
 
     def barrier():
         if world > 1:
@@ -411,9 +412,10 @@ def run_ours(args):
     e_start.record()
     for k in range(K):
         ev[k][0].record()
-        w.warp_rgbd(rgb, depth, g, a)
+        p = w.prepare(g, a)
+        w.warp_rgbd(rgb, depth, params=p)
         ev[k][1].record()
-        w.unwarp_normals(normals, g, a)
+        w.unwarp_normals(normals, params=p)
         ev[k][2].record()
     e_end.record()
     barrier()

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define VIDC_ABI_VERSION 2
+#define VIDC_ABI_VERSION 3
 
 typedef enum vidc_status {
     VIDC_OK = 0,
@@ -140,6 +140,15 @@ int vidc_warp_rgb_sparse_depth(const vidc_camera *cam, const vidc_image *rgb, co
    d_Ig, d_Ia: (B,3) contiguous.  d_params: B entries. One thread per frame, no host sync. */
 int vidc_frame_params_compute(const vidc_camera *cam, const float *d_Ig, const float *d_Ia, int32_t B,
                               vidc_frame_params *d_params, void *stream);
+
+/* Parameters computed ONCE for a batch and shared by the forward and the inverse entry points (the reference rebuilds them in
+   every call, :124 and :225, from the same I_g / I_a): fills d_params_ws (vidc_workspace_bytes(cam, B) bytes) with everything
+   vidc_warp_rgbd, vidc_warp_rgb_sparse_depth and vidc_unwarp_normals need -- frame parameters, the forward kernels' exterior-tile
+   bitmap and prefetch boxes, the inverse kernels' division proof -- and, if d_H_out is not NULL, Cg_H_C (B,3,3).  Those entry
+   points then take d_Ig = d_Ia = NULL: "d_params_ws is prepared" (same camera, same B, written earlier in stream order; the
+   call does not launch a per-frame kernel and leaves d_params_ws untouched, so it may be shared by any number of calls). */
+int vidc_frame_params_prepare(const vidc_camera *cam, const float *d_Ig, const float *d_Ia, int32_t B,
+                              vidc_frame_params *d_params_ws, float *d_H_out, void *stream);
 
 /* _build_homography's return tuple (:58): scatters params into three contiguous (B,3,3) tensors.
    Any of d_H, d_R, d_Hinv may be NULL. */

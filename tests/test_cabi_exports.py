@@ -23,7 +23,7 @@ def test_header_symbols_are_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), f"{n} is declared in include/vidc_b200.h but not exported"
     assert set(names) == set(_cabi.EXPORTED_SYMBOLS), "ctypes binding and header disagree"
-    assert lib.vidc_abi_version() == 2
+    assert lib.vidc_abi_version() == 3
 
 
 def test_struct_layouts_match_header():
@@ -98,3 +98,13 @@ def test_torch_extension_builds_and_registers_its_operators():
     outs = torch.ops.vidc.warp_rgbd(x, x[:, :1], g, g, 202., 202., 159.93827, 119.938015, 1)
     assert [tuple(o.shape) for o in outs] == [(2, 3, 3), (2, 3, 240, 320), (2, 1, 240, 320), (2, 1, 240, 320)] and outs[3].dtype == torch.uint8
     assert len(torch.ops.vidc.build_homography(g, g, 202., 202., 159.93827, 119.938015)) == 3
+    # parameters prepared once per batch: the Meta workspace has the size the library asks for
+    import ctypes
+    from vi_depth_completion_b200 import _cabi
+    cam = _cabi.VidcCamera()
+    _cabi.lib().vidc_camera_init(202., 202., 159.93827, 119.938015, ctypes.byref(cam))
+    ws, H = torch.ops.vidc.frame_params(g, g, 202., 202., 159.93827, 119.938015)
+    assert ws.numel() * 4 == _cabi.lib().vidc_workspace_bytes(ctypes.byref(cam), 2) and H.shape == (2, 3, 3)
+    outs = torch.ops.vidc.warp_rgbd_prepared(x, x[:, :1], ws, 202., 202., 159.93827, 119.938015, 0)
+    assert [tuple(o.shape) for o in outs] == [(2, 3, 240, 320), (2, 1, 240, 320), (2, 1, 240, 320)]
+    assert torch.ops.vidc.unwarp_normals_prepared(x, ws, 202., 202., 159.93827, 119.938015, True).shape == (2, 3, 240, 320)

@@ -106,3 +106,44 @@ def test_host_time_per_call(cuda_device):
             _torchops._state.update(saved)
     print(f"host us per step (warp_rgbd + unwarp_normals, B=1): extension {res['torch']:.1f}, ctypes {res['ctypes']:.1f}")
     assert res["torch"] < res["ctypes"]
+
+
+@pytest.mark.parametrize("frontend", ["torch", "ctypes"])
+def test_parameters_prepared_once_per_batch(cuda_device, frontend):
+    """prepare() + warp_rgbd(params=) + unwarp_normals(params=): one per-frame kernel for the batch instead of one per call
+    (the reference rebuilds the homographies in every call, :124 and :225).  Same bits as the calls that take I_g / I_a, through
+    the extension and through ctypes; two launches saved per step; the handle is checked (camera, batch, device)."""
+    import torch
+    from vi_depth_completion_b200 import _cabi, _torchops
+    from vi_depth_completion_b200.warping_2dof_alignment import Warping2DOFAlignment
+    w, rgb, depth, normals, g, a = _setup(cuda_device, B=5)
+    saved = dict(_torchops._state)
+    if frontend == "ctypes":
+        _torchops._state.update(tried=True, ops=None)
+    try:
+        H0, r0, d0, m0 = w.warp_rgbd(rgb, depth, g, a)
+        _, z0 = w.unwarp_normals(normals, g, a)
+        _, zr0 = w.unwarp_normals(normals, g, a, normalize=False)
+        n0 = _cabi.lib().vidc_launch_count()
+        p = w.prepare(g, a)
+        H1, r1, d1, m1 = w.warp_rgbd(rgb, depth, params=p)
+        H2, z1 = w.unwarp_normals(normals, params=p)
+        _, zr1 = w.unwarp_normals(normals, params=p, normalize=False)
+        assert _cabi.lib().vidc_launch_count() - n0 == 4                    # 1 per-frame kernel + 3 warps
+        for x, y in ((H0, H1), (H0, H2), (r0, r1), (d0, d1), (m0, m1), (z0, z1), (zr0, zr1)):
+            assert torch.equal(x, y)
+        assert depth.dim() == 3 and d1.dim() == 3                            # 3-D depth in, 3-D depth out (:110-112, :153-154)
+        d4 = w.warp_rgbd(rgb, depth[:, None], params=p)[2]
+        assert d4.dim() == 4 and torch.equal(d4[:, 0], d0)
+        with pytest.raises(AssertionError):
+            w.warp_rgbd(rgb[:3], depth[:3], params=p)                        # batch of the handle
+        with pytest.raises(RuntimeError):
+            Warping2DOFAlignment(404., 404., 319.87654, 239.87603).unwarp_normals(normals, params=p)   # another camera
+        with pytest.raises(RuntimeError):
+            w.unwarp_normals(normals)                                        # neither gravity nor params
+        x = rgb.clone().requires_grad_(True)
+        out = w.warp_rgbd(x, depth, params=p)
+        with pytest.raises(NotImplementedError):
+            out[1].sum().backward()
+    finally:
+        _torchops._state.update(saved)

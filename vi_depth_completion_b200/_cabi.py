@@ -78,6 +78,7 @@ _SIGNATURES = {
                                                  _P(VidcImage), ctypes.c_void_p]),
     "vidc_warp_unwarp_host": (ctypes.c_int, [_P(VidcCamera), ctypes.c_int32] + [ctypes.c_void_p] * 10),
     "vidc_release_workspace": (ctypes.c_int, []),
+    "vidc_frame_params_prepare": (ctypes.c_int, [_P(VidcCamera), c_f32p, c_f32p, ctypes.c_int32, ctypes.c_void_p, c_f32p, ctypes.c_void_p]),
     "vidc_to_tensor_u8": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int32] * 4 + [c_f32p, ctypes.c_void_p]),
     "vidc_warp_unwarp_host_u8": (ctypes.c_int, [_P(VidcCamera), ctypes.c_int32] + [ctypes.c_void_p] * 10),
     "vidc_condition_gravity": (ctypes.c_int, [c_f32p, ctypes.c_int32, ctypes.c_int32, c_f32p, c_f32p, ctypes.c_void_p]),
@@ -107,8 +108,8 @@ def lib():
             fn = getattr(l, name)  # AttributeError if the library does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if l.vidc_abi_version() != 2:
-            raise RuntimeError(f"libvidc_b200.so ABI version {l.vidc_abi_version()} != 2; rebuild it")
+        if l.vidc_abi_version() != 3:
+            raise RuntimeError(f"libvidc_b200.so ABI version {l.vidc_abi_version()} != 3; rebuild it")
         _lib = l
     return _lib
 

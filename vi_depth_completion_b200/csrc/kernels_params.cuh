@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(320) frame_params_tiles_kernel(vidc_camera cam
         p.fwd_col_major = fabsf(p.Hinv[1] * p.ikh) > 4.0f * fabsf(p.Hinv[0] * p.ikw) ? 1.0f : 0.0f;
         p.inv_col_major = fabsf(p.H[1]) > 4.0f * fabsf(p.H[0]) ? 1.0f : 0.0f;
 #pragma unroll
-        for (int k = 0; k < 11; ++k) p.reserved[k] = 0.0f;
+        for (int k = 0; k < 10; ++k) p.reserved[k] = 0.0f;
+        p.reserved[10] = vidc::inv_division_proven(p, cam) ? 1.0f : 0.0f;      // as frame_params_kernel: prepared workspaces serve both directions
         sp = p;
     }
     __syncthreads();
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(320) frame_params_tiles_kernel(vidc_camera cam
     const float* spf = reinterpret_cast<const float*>(&sp);
     if (t < 37) o[t] = spf[t];                                       // everything before reserved[]
     if ((t & 31) == 0) o[37 + (t >> 5)] = __uint_as_float(bal);      // reserved[0..9]: 320 tile bits
-    if (t == 1) o[47] = 0.0f;                                        // reserved[10]
+    if (t == 1) o[47] = sp.reserved[10];
     if (H_out && t < 9) H_out[9 * i + t] = sp.H[t];
     if (src_boxes) {                                                 // prefetch hints of the sheared forward kernels
         for (int k = t; k < nt; k += blockDim.x) {

@@ -128,6 +128,56 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor> warp_rgbd(const at::T
     return {Hm, rgb_w, depth_w, mask};
 }
 
+// ---- parameters prepared once per batch and shared by both directions (vidc_frame_params_prepare) ---------------------------------
+std::tuple<at::Tensor, at::Tensor> frame_params(const at::Tensor& I_g, const at::Tensor& I_a, double fx, double fy, double cx, double cy) {
+    check_f32_cuda(I_g, "I_g");
+    const vidc_camera cam = make_camera(fx, fy, cx, cy);
+    const c10::cuda::CUDAGuard guard(I_g.device());
+    auto [g, a] = gravity(I_g, I_a, I_g.device());
+    at::Tensor ws = workspace(cam, g.size(0), g.options());
+    at::Tensor Hm = at::empty({g.size(0), 3, 3}, g.options());
+    check_status(vidc_frame_params_prepare(&cam, g.data_ptr<float>(), a.data_ptr<float>(), (int32_t)g.size(0),
+                                           reinterpret_cast<vidc_frame_params*>(ws.data_ptr<float>()), Hm.data_ptr<float>(),
+                                           at::cuda::getCurrentCUDAStream().stream()));
+    return {ws, Hm};
+}
+void check_prepared(const at::Tensor& ws, const vidc_camera& cam, int64_t B, const at::Device& dev) {
+    check_f32_cuda(ws, "params");
+    TORCH_CHECK(ws.device() == dev, "params must live on ", dev, ", got ", ws.device());
+    TORCH_CHECK(ws.is_contiguous() && (size_t)ws.numel() * 4 >= vidc_workspace_bytes(&cam, (int32_t)std::max<int64_t>(B, 1)),
+                "params: not a workspace prepared by prepare() for ", B, " frames of this camera");
+}
+std::tuple<at::Tensor, at::Tensor, at::Tensor> warp_rgbd_prepared(const at::Tensor& rgb, const at::Tensor& depth, const at::Tensor& ws,
+                                                                  double fx, double fy, double cx, double cy, int64_t depth_mode) {
+    check_f32_cuda(rgb, "x_rgb");
+    check_f32_cuda(depth, "x_depth");
+    TORCH_CHECK(rgb.dim() == 4 && depth.dim() == 4, "warp_rgbd: expected (B,3,h,w) and (B,1,h,w)");
+    TORCH_CHECK(depth.device() == rgb.device(), "x_depth must live on ", rgb.device(), ", got ", depth.device());
+    const vidc_camera cam = make_camera(fx, fy, cx, cy);
+    const c10::cuda::CUDAGuard guard(rgb.device());
+    check_prepared(ws, cam, rgb.size(0), rgb.device());
+    at::Tensor rgb_w = canvas_like(rgb, cam), depth_w = canvas_like(depth, cam);
+    at::Tensor mask = at::empty({rgb.size(0), 1, cam.H, cam.W}, rgb.options().dtype(at::kByte));
+    const vidc_image ri = image_of(rgb), di = image_of(depth), rwi = image_of(rgb_w), dwi = image_of(depth_w);
+    check_status(vidc_warp_rgbd(&cam, &ri, &di, nullptr, nullptr, (int32_t)rgb.size(0), (vidc_interp)depth_mode,
+                                reinterpret_cast<vidc_frame_params*>(ws.data_ptr<float>()), nullptr, &rwi, &dwi,
+                                mask.data_ptr<uint8_t>(), nullptr, at::cuda::getCurrentCUDAStream().stream()));
+    return {rgb_w, depth_w, mask};
+}
+at::Tensor unwarp_normals_prepared(const at::Tensor& x, const at::Tensor& ws, double fx, double fy, double cx, double cy, bool normalize) {
+    check_f32_cuda(x, "x");
+    TORCH_CHECK(x.dim() == 4, "x: expected a 4-D tensor, got ", x.dim(), "-D");
+    const vidc_camera cam = make_camera(fx, fy, cx, cy);
+    const c10::cuda::CUDAGuard guard(x.device());
+    check_prepared(ws, cam, x.size(0), x.device());
+    at::Tensor z = canvas_like(x, cam);
+    const vidc_image xi = image_of(x), zi = image_of(z);
+    check_status(vidc_unwarp_normals(&cam, &xi, nullptr, nullptr, (int32_t)x.size(0), normalize ? 1 : 0,
+                                     reinterpret_cast<vidc_frame_params*>(ws.data_ptr<float>()), nullptr, &zi, nullptr,
+                                     at::cuda::getCurrentCUDAStream().stream()));
+    return z;
+}
+
 // ---- _build_homography (:35-58) ------------------------------------------------------------------------------------------------
 std::tuple<at::Tensor, at::Tensor, at::Tensor> build_homography(const at::Tensor& I_g, const at::Tensor& I_a, double fx, double fy,
                                                                 double cx, double cy) {
@@ -163,6 +213,21 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor> warp_rgbd_meta(const 
     return {at::empty({I_g.size(0), 3, 3}, rgb.options()), canvas_like_hw(rgb, H, W), canvas_like_hw(depth, H, W),
             at::empty({rgb.size(0), 1, H, W}, rgb.options().dtype(at::kByte))};
 }
+int64_t workspace_floats_meta(double cx, double cy, int64_t B) {            // as vidc_workspace_bytes: 192 B per frame + 16 B per tile
+    const int64_t tiles = ((canvas_w(cx) + 31) / 32) * ((canvas_h(cy) + 31) / 32), n = std::max<int64_t>(B, 1);
+    return (n * 192 + n * tiles * 16 + 3) / 4;
+}
+std::tuple<at::Tensor, at::Tensor> frame_params_meta(const at::Tensor& I_g, const at::Tensor&, double, double, double cx, double cy) {
+    return {at::empty({workspace_floats_meta(cx, cy, I_g.size(0))}, I_g.options()), at::empty({I_g.size(0), 3, 3}, I_g.options())};
+}
+std::tuple<at::Tensor, at::Tensor, at::Tensor> warp_rgbd_prepared_meta(const at::Tensor& rgb, const at::Tensor& depth, const at::Tensor&,
+                                                                       double, double, double cx, double cy, int64_t) {
+    const int64_t H = canvas_h(cy), W = canvas_w(cx);
+    return {canvas_like_hw(rgb, H, W), canvas_like_hw(depth, H, W), at::empty({rgb.size(0), 1, H, W}, rgb.options().dtype(at::kByte))};
+}
+at::Tensor unwarp_normals_prepared_meta(const at::Tensor& x, const at::Tensor&, double, double, double cx, double cy, bool) {
+    return canvas_like_hw(x, canvas_h(cy), canvas_w(cx));
+}
 std::tuple<at::Tensor, at::Tensor, at::Tensor> build_homography_meta(const at::Tensor& I_g, const at::Tensor&, double, double, double, double) {
     auto t = [&] { return at::empty({I_g.size(0), 3, 3}, I_g.options()); };
     return {t(), t(), t()};
@@ -176,16 +241,26 @@ TORCH_LIBRARY(vidc, m) {
     m.def("warp_rgbd(Tensor rgb, Tensor depth, Tensor I_g, Tensor I_a, float fx, float fy, float cx, float cy, int depth_mode) -> "
           "(Tensor, Tensor, Tensor, Tensor)");
     m.def("build_homography(Tensor I_g, Tensor I_a, float fx, float fy, float cx, float cy) -> (Tensor, Tensor, Tensor)");
+    m.def("frame_params(Tensor I_g, Tensor I_a, float fx, float fy, float cx, float cy) -> (Tensor, Tensor)");
+    m.def("warp_rgbd_prepared(Tensor rgb, Tensor depth, Tensor params, float fx, float fy, float cx, float cy, int depth_mode) -> "
+          "(Tensor, Tensor, Tensor)");
+    m.def("unwarp_normals_prepared(Tensor x, Tensor params, float fx, float fy, float cx, float cy, bool normalize) -> Tensor");
 }
 TORCH_LIBRARY_IMPL(vidc, CUDA, m) {
     m.impl("warp_forward", &warp_forward);
     m.impl("unwarp_normals", &unwarp_normals);
     m.impl("warp_rgbd", &warp_rgbd);
     m.impl("build_homography", &build_homography);
+    m.impl("frame_params", &frame_params);
+    m.impl("warp_rgbd_prepared", &warp_rgbd_prepared);
+    m.impl("unwarp_normals_prepared", &unwarp_normals_prepared);
 }
 TORCH_LIBRARY_IMPL(vidc, Meta, m) {
     m.impl("warp_forward", &warp_forward_meta);
     m.impl("unwarp_normals", &unwarp_normals_meta);
     m.impl("warp_rgbd", &warp_rgbd_meta);
     m.impl("build_homography", &build_homography_meta);
+    m.impl("frame_params", &frame_params_meta);
+    m.impl("warp_rgbd_prepared", &warp_rgbd_prepared_meta);
+    m.impl("unwarp_normals_prepared", &unwarp_normals_prepared_meta);
 }

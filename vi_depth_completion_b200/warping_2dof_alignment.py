@@ -144,6 +144,15 @@ def _check_interp_mode(interp_mode, allow_bicubic=False):
                      f"but got: '{interp_mode}'")
 
 
+class FrameParams:
+    """Per-frame parameters of one batch, prepared once (Warping2DOFAlignment.prepare) and shared by warp_rgbd and
+    unwarp_normals: the reference rebuilds them in every call (:124, :225) from the same I_g / I_a.  `H` is Cg_H_C (B,3,3)."""
+    __slots__ = ("ws", "H", "B", "device", "intr")
+
+    def __init__(self, ws, H, intr):
+        self.ws, self.H, self.B, self.device, self.intr = ws, H, H.shape[0], H.device, intr
+
+
 class Warping2DOFAlignment:
     # networks/warping_2dof_alignment.py:6
     def __init__(self, fx=577.87061 * 0.5, fy=577.87061 * 0.5, cx=319.87654 * 0.5, cy=239.87603 * 0.5):
@@ -354,13 +363,68 @@ class Warping2DOFAlignment:
         return Cg_H_C, _attach(x, y)
 
     # ---- additive fused entry points ------------------------------------
-    def warp_rgbd(self, x_rgb, x_depth, I_g, I_a, depth_mode='bilinear', with_mask=True, with_coverage=False):
+    def prepare(self, I_g, I_a):
+        """Everything the two fused entry points need per frame (homographies, canvas scale, the kernels' per-tile tables),
+        computed ONCE for a batch: pass the result as `params=` to warp_rgbd and unwarp_normals, which then launch no
+        per-frame kernel of their own.  Valid for this camera and these I_g / I_a values."""
+        ops = _torchops.ops()
+        if ops is not None and isinstance(I_g, torch.Tensor) and isinstance(I_a, torch.Tensor):
+            ws, H = _op(ops.frame_params, I_g, I_a, *self._intr)
+            return FrameParams(ws, H, self._intr)
+        _require_cuda_f32(I_g, "I_g")
+        device = I_g.device
+        g, a = _gravity(I_g, I_a, device)
+        ws = self._params_ws(g.shape[0], device)
+        H = torch.empty((g.shape[0], 3, 3), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            check(lib().vidc_frame_params_prepare(ctypes.byref(self._cam), g.data_ptr(), a.data_ptr(), g.shape[0], ws.data_ptr(),
+                                                  H.data_ptr(), _stream_ptr(device)))
+        return FrameParams(ws, H, self._intr)
+
+    def _prepared(self, params, x, name):
+        if not isinstance(params, FrameParams):
+            raise RuntimeError("params: expected the result of prepare()")
+        if params.intr != self._intr:
+            raise RuntimeError("params were prepared for a different camera")
+        if params.device != x.device:
+            raise RuntimeError(f"params live on {params.device}, {name} on {x.device}")
+        if params.B != x.shape[0]:
+            raise AssertionError(f"{name}.shape[0]={x.shape[0]} != I_g.shape[0]={params.B}")
+        return params
+
+    def warp_rgbd(self, x_rgb, x_depth, I_g=None, I_a=None, depth_mode='bilinear', with_mask=True, with_coverage=False, params=None):
         """One pass: warp RGB (B,3,h,w) and sparse depth (B,h,w)/(B,1,h,w) into the gravity-aligned canvas and
-        emit the validity mask of surface_normal.py:151.  Returns (Cg_H_C, rgb_w, depth_w, mask_u8[, coverage])."""
+        emit the validity mask of surface_normal.py:151.  Returns (Cg_H_C, rgb_w, depth_w, mask_u8[, coverage]).
+        params=prepare(I_g, I_a) instead of I_g / I_a: no per-frame kernel in this call."""
         _check_interp_mode(depth_mode)
         _require_cuda_f32(x_rgb, "x_rgb")
         device = x_rgb.device
         ops = _torchops.ops()
+        if params is not None:
+            if x_rgb.dim() != 4 or not isinstance(x_depth, torch.Tensor) or not with_mask or with_coverage:
+                raise RuntimeError("warp_rgbd(params=...): RGB (B,3,h,w) + depth, mask on, no coverage")
+            p = self._prepared(params, x_rgb, "x_rgb")
+            _require_cuda_f32(x_depth, "x_depth")
+            d4 = x_depth.view(x_depth.shape[0], 1, x_depth.shape[1], x_depth.shape[2]) if x_depth.dim() == 3 else x_depth
+            mode = _cabi.VIDC_BILINEAR if depth_mode == "bilinear" else _cabi.VIDC_NEAREST
+            if ops is not None:
+                rgb_w, depth_w, mask = _op(ops.warp_rgbd_prepared, x_rgb.detach() if x_rgb.requires_grad else x_rgb,
+                                           d4.detach() if d4.requires_grad else d4, p.ws, *self._intr, mode)
+            else:
+                if d4.device != device:
+                    raise RuntimeError(f"x_depth must live on {device}, got {d4.device}")
+                rgb_w, depth_w = self._empty_like_canvas(x_rgb), self._empty_like_canvas(d4)
+                mask = torch.empty((x_rgb.shape[0], 1, int(self.H), int(self.W)), dtype=torch.uint8, device=device)
+                ri, di, rwi, dwi = _image(x_rgb), _image(d4), _image(rgb_w), _image(depth_w)
+                with torch.cuda.device(device):
+                    check(lib().vidc_warp_rgbd(ctypes.byref(self._cam), ctypes.byref(ri), ctypes.byref(di), None, None, p.B, mode,
+                                               p.ws.data_ptr(), None, ctypes.byref(rwi), ctypes.byref(dwi), mask.data_ptr(), None,
+                                               _stream_ptr(device)))
+            if x_depth.dim() == 3:
+                depth_w = depth_w.view(depth_w.shape[0], depth_w.shape[2], depth_w.shape[3])
+            return p.H, _attach(x_rgb, rgb_w), _attach(x_depth, depth_w), mask
+        if I_g is None or I_a is None:
+            raise RuntimeError("warp_rgbd: pass I_g and I_a, or params=prepare(I_g, I_a)")
         if (ops is not None and with_mask and not with_coverage and isinstance(x_depth, torch.Tensor) and x_rgb.dim() == 4
                 and isinstance(I_g, torch.Tensor) and isinstance(I_a, torch.Tensor)):
             d4 = x_depth.view(x_depth.shape[0], 1, x_depth.shape[1], x_depth.shape[2]) if x_depth.dim() == 3 else x_depth
@@ -462,8 +526,26 @@ class Warping2DOFAlignment:
         out = (Cg_H_C, _attach(x_rgbd, y), mask)                                   # forward-only
         return out + (cov,) if with_coverage else out
 
-    def unwarp_normals(self, y, I_g, I_a, normalize=True, with_valid=False):
+    def unwarp_normals(self, y, I_g=None, I_a=None, normalize=True, with_valid=False, params=None):
         """One pass: inverse warp + R^T rotation + F.normalize(dim=1) (surface_normal.py:169-170).
-        Returns (Cg_H_C, n_hat[, valid_u8])."""
+        Returns (Cg_H_C, n_hat[, valid_u8]).  params=prepare(I_g, I_a) instead of I_g / I_a: no per-frame kernel here."""
+        if params is not None:
+            _require_cuda_f32(y, "x")
+            if y.dim() != 4 or with_valid:
+                raise RuntimeError("unwarp_normals(params=...): a 4-D image, no validity output")
+            p = self._prepared(params, y, "x")
+            needs_graph = torch.is_grad_enabled() and y.requires_grad
+            ops = _torchops.ops()
+            if ops is not None:
+                z = _op(ops.unwarp_normals_prepared, y.detach() if needs_graph else y, p.ws, *self._intr, bool(normalize))
+            else:
+                z = self._empty_like_canvas(y)
+                yi, zi = _image(y), _image(z)
+                with torch.cuda.device(y.device):
+                    check(lib().vidc_unwarp_normals(ctypes.byref(self._cam), ctypes.byref(yi), None, None, p.B, 1 if normalize else 0,
+                                                    p.ws.data_ptr(), None, ctypes.byref(zi), None, _stream_ptr(y.device)))
+            return p.H, (_attach(y, z) if needs_graph else z)           # forward-only with a prepared workspace
+        if I_g is None or I_a is None:
+            raise RuntimeError("unwarp_normals: pass I_g and I_a, or params=prepare(I_g, I_a)")
         H, z, valid = self._unwarp(y, I_g, I_a, normalize=normalize, want_valid=with_valid)
         return (H, z, valid) if with_valid else (H, z)
