@@ -438,6 +438,78 @@ warp_planes_shear_kernel(const __grid_constant__ PlanesArgs a, const __grid_cons
     warp_planes_shear_write_out<GW, GH, C, false>(a, tile);
 }
 
+// ---- packed fp32x2 forms for the inverse warp (VIDC_SHEAR_PACKED) --------------------------------------------------------------
+// The inverse kernel is bound by issue slots (81 % issue-active with the TMA write-out).  Blackwell's FFMA2 / FMUL2 / FADD2 do
+// two independent fp32 operations per lane and instruction, each rounded exactly like its scalar form, so pairing the (u, v)
+// halves of the coordinate chain, two of the three planes of the interpolation and of the rotation, and the divisions that
+// share a reciprocal removes instructions without moving a bit -- with the one hazard kernels_fast.cuh documents (ptxas fuses
+// a packed multiply that feeds a packed add into FFMA2 even under -fmad=false): such multiplies stay scalar.
+// Measured (profiles/r2_history.md): 0.4479 -> 0.4411 ms for the inverse (the register pairing costs ~85 moves per kernel, about
+// half of what the packed operations save); packing only the coordinate chain, or the chain and the rotation, spills at 32
+// registers and is slower (0.475 / 0.488 ms).  -DVIDC_SHEAR_PACKED=0 restores the scalar form (same bits).
+#ifndef VIDC_SHEAR_PACKED
+#define VIDC_SHEAR_PACKED 1
+#endif
+#ifndef VIDC_SHEAR_PACKED_SAMPLE
+#define VIDC_SHEAR_PACKED_SAMPLE 1
+#endif
+#ifndef VIDC_SHEAR_PACKED_ROT
+#define VIDC_SHEAR_PACKED_ROT 1
+#endif
+__device__ __forceinline__ float2 div2p_sel(float2 uv, float s, bool proven) {       // packed div2_sel
+    const float r = rcp_refined(s);
+    float2 q = mul2(uv, bc(r));
+    const float2 rem = fma2(bc(-s), q, uv);
+    q = fma2(rem, bc(r), q);
+    if (!proven) {                                                 // CTA-uniform
+        const float as = fabsf(s);
+        const float hi = fmaxf(fmaxf(fabsf(uv.x), fabsf(uv.y)), as * 0x1p40f);
+        const float lo = fminf(fminf(fabsf(uv.x), fabsf(uv.y)), as * 0x1p-40f);
+        if (!(lo >= 0x1p-80f && hi <= 0x1p80f)) {
+            q.x = ieee_div_slow(uv.x, s);
+            q.y = ieee_div_slow(uv.y, s);
+        }
+    }
+    return q;
+}
+__device__ __forceinline__ void normalize3p_rn(float2& z01, float& z2) {             // packed normalize3_rn
+    const float2 sq = mul2(z01, z01);
+    const float ss = (sq.x + sq.y) + z2 * z2;
+    float rs;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(ss));
+    const float s = ss * rs, h = rs * 0.5f;
+    const float n = fmaf(fmaf(-s, s, ss), h, s);
+    const float r = rcp_refined(n);
+    float2 q = mul2(z01, bc(r));
+    const float2 rem = fma2(bc(-n), q, z01);
+    q = fma2(rem, bc(r), q);
+    const float q2 = div_with_rcp(z2, n, r);
+    const unsigned k0 = __float_as_uint(z01.x) * 2u - 1u, k1 = __float_as_uint(z01.y) * 2u - 1u, k2 = __float_as_uint(z2) * 2u - 1u;
+    const bool comps_ok = min(min(k0, k1), k2) >= 0x42ffffffu;
+    const bool ss_ok = (__float_as_uint(ss) - 0x21800000u) <= 0x3c000000u;
+    if (comps_ok && ss_ok) {
+        z01 = q; z2 = q2;
+    } else {
+        const float ns = ieee_norm_slow(ss);
+        z01.x = ieee_div_slow(z01.x, ns); z01.y = ieee_div_slow(z01.y, ns); z2 = ieee_div_slow(z2, ns);
+    }
+}
+__device__ __forceinline__ Px3 inv_sample_row_lazy_p(const float* __restrict__ in, int x_sh, int x_sc, int H, int W, const Pos& t0) {
+    Px3 o = {0.0f, 0.0f, 0.0f};
+    if (__all_sync(0xffffffffu, t0.interior)) {
+        o = inv_sample_interior_p(in, x_sh, x_sc, t0);
+    } else {
+        Pos t = t0;
+        t.touch = t0.fin && (unsigned)(t0.x0 + 1) <= (unsigned)W && (unsigned)(t0.y0 + 1) <= (unsigned)H;
+        if (__any_sync(0xffffffffu, t.touch)) {
+            o.a = sample_border(in, x_sh, H, W, t);
+            o.b = sample_border(in + x_sc, x_sh, H, W, t);
+            o.c = sample_border(in + 2 * x_sc, x_sh, H, W, t);
+        }
+    }
+    return o;
+}
+
 // ---- inverse: camera px -> canvas coords, 3 planes, R^T, renormalisation ------------------------------------------------
 // The fourth component of the staging slot carries the optional validity flag.
 template <int GW, int GH, bool NORMALIZE, bool HAS_VALID, bool ALONG_Y, bool PLANAR = false>
@@ -457,6 +529,38 @@ __device__ __forceinline__ void unwarp_normals_shear_segments(const InvArgs& a, 
 #pragma unroll
     for (int j = 0; j < ROWS_PER_THREAD; ++j) {
         const int S = (VIDC_SEG(warp, j) + sh_l) & 31;
+#if VIDC_SHEAR_PACKED
+        float s;
+        float2 uv;
+        if (ALONG_Y) {
+            const float Xf = (float)(tileX0 + S);
+            s = fmaf(Hm[7], c_fix, Hm[6] * Xf) + Hm[8];
+            uv = add2(fma2(f2(Hm[1], Hm[4]), bc(c_fix), f2(Hm[0] * Xf, Hm[3] * Xf)), f2(Hm[2], Hm[5]));
+        } else {
+            const float Yf = (float)(tileY0 + S);
+            s = fmaf(Hm[7], Yf, s0) + Hm[8];
+            uv = add2(fma2(f2(Hm[1], Hm[4]), bc(Yf), f2(u0, v0)), f2(Hm[2], Hm[5]));
+        }
+        const float2 txy = div2p_sel(uv, s, proven);               // :245
+        const float2 tm = sub2(txy, f2(px_min, py_min));
+        const float2 cm = sub2(f2(kw * tm.x, kh * tm.y), f2(a.cam.cx, a.cam.cy));              // scalar multiplies: see above
+        const float2 g1 = add2(f2(a.cam.inv_half_w * cm.x, a.cam.inv_half_h * cm.y), bc(1.0f));
+        const float2 ixy = mul2(fma2(g1, f2(Wf, Hf), bc(-1.0f)), bc(0.5f));                    // ATen unnormalise
+        const Pos t = make_pos_p(ixy, H, W);
+        const Px3 y = HAS_VALID ? inv_sample_row(in, W, W * H, H, W, t)
+                                : (VIDC_SHEAR_PACKED_SAMPLE ? inv_sample_row_lazy_p(in, W, W * H, H, W, t) : inv_sample_row_lazy(in, W, W * H, H, W, t));
+#if VIDC_SHEAR_PACKED_ROT
+        float2 z01 = fma2(f2(R[6], R[7]), bc(y.c), fma2(f2(R[3], R[4]), bc(y.b), fma2(f2(R[0], R[1]), bc(y.a), bc(0.0f))));   // :253
+        float z2 = fmaf(R[8], y.c, fmaf(R[5], y.b, fmaf(R[2], y.a, 0.0f)));
+        if (NORMALIZE) normalize3p_rn(z01, z2);                    // surface_normal.py:170
+        const float z0 = z01.x, z1 = z01.y;
+#else
+        float z0 = fmaf(R[6], y.c, fmaf(R[3], y.b, fmaf(R[0], y.a, 0.0f)));
+        float z1 = fmaf(R[7], y.c, fmaf(R[4], y.b, fmaf(R[1], y.a, 0.0f)));
+        float z2 = fmaf(R[8], y.c, fmaf(R[5], y.b, fmaf(R[2], y.a, 0.0f)));
+        if (NORMALIZE) normalize3_rn(z0, z1, z2);
+#endif
+#else
         float u, v, s;
         if (ALONG_Y) {
             const float Xf = (float)(tileX0 + S);
@@ -482,6 +586,7 @@ __device__ __forceinline__ void unwarp_normals_shear_segments(const InvArgs& a, 
         float z1 = fmaf(R[7], y.c, fmaf(R[4], y.b, fmaf(R[1], y.a, 0.0f)));
         float z2 = fmaf(R[8], y.c, fmaf(R[5], y.b, fmaf(R[2], y.a, 0.0f)));
         if (NORMALIZE) normalize3_rn(z0, z1, z2);                  // surface_normal.py:170
+#endif
         if (PLANAR) {
             tp[0][S][lane] = z0;
             tp[1][S][lane] = z1;
