@@ -155,6 +155,11 @@ int vidc_frame_params_prepare(const vidc_camera *cam, const float *d_Ig, const f
 int vidc_build_homography(const vidc_camera *cam, const float *d_Ig, const float *d_Ia, int32_t B,
                           float *d_H, float *d_R, float *d_Hinv, void *stream);
 
+/* Layouts and speed (results never depend on them): contiguous NCHW planes whose width is a multiple of 32 and 16-byte aligned
+   outputs (and mask) run the sheared kernels with the TMA write-out (bulk tensor stores, one output tensor map per call);
+   outputs a tensor map cannot describe take the same kernels' LSU write-out; everything else -- channels-last or otherwise
+   strided tensors, other widths -- is accepted without a copy by the strided kernels (about half the speed). */
+
 /* Replaces warp_with_gravity_center_aligned (:108-156): fused params + grid + grid_sample.
    x: (B,C,Hin,Win) any strides; y: (B,C,cam.H,cam.W).  d_H_out (B,3,3) may be NULL.
    d_params_ws: caller-owned scratch of vidc_workspace_bytes(cam, B) bytes (B vidc_frame_params first; may alias across calls). */
