@@ -57,13 +57,32 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 // generic proxy fences (fence_async_smem) before the barrier; one thread then issues the stores, commits the group and waits
 // until the TMA unit has READ the tile (the CTA must not exit -- and hand its shared memory to the next CTA -- earlier).
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#ifndef VIDC_TMA_STORE_HINT
+#define VIDC_TMA_STORE_HINT 0     // 1: L2::evict_first on the stores (the outputs are never re-read by these kernels): measured neutral
+                                  // (forward 0.4934 / 0.4925 ms, inverse 0.4392 / 0.4397 ms, bench 271.9 / 271.6 K frames/s), so off
+#endif
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int x, int y, int c, int n) {
+#if VIDC_TMA_STORE_HINT
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;"
+                 ::"l"((unsigned long long)map), "r"(smem_u32(smem_src)), "r"(x), "r"(y), "r"(c), "r"(n), "l"(l2_evict_first_policy()) : "memory");
+#else
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                  ::"l"((unsigned long long)map), "r"(smem_u32(smem_src)), "r"(x), "r"(y), "r"(c), "r"(n) : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int x, int y, int n) {
+#if VIDC_TMA_STORE_HINT
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
+                 ::"l"((unsigned long long)map), "r"(smem_u32(smem_src)), "r"(x), "r"(y), "r"(n), "l"(l2_evict_first_policy()) : "memory");
+#else
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
                  ::"l"((unsigned long long)map), "r"(smem_u32(smem_src)), "r"(x), "r"(y), "r"(n) : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_store_commit_and_wait_read() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
