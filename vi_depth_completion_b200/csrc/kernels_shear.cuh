@@ -178,6 +178,7 @@ __device__ __forceinline__ unsigned int warp_rgbd_shear_segments(const FwdArgs& 
             tp[1][S][lane] = o.g;
             tp[2][S][lane] = o.b;
             if (HAS_D) tp[3][S][lane] = o.d;
+            else if (a.dep_o) tp[3][S][lane] = 0.0f;               // sparse-depth route: the zero fill of the depth plane rides along
             if (a.mask || a.coverage) {                            // surface_normal.py:151
                 const unsigned int m = (o.r + o.g) + o.b > 0.01f;
                 mt[S][lane] = (unsigned char)m;
@@ -281,7 +282,7 @@ warp_rgbd_shear_kernel(const __grid_constant__ FwdArgs a, const __grid_constant_
         fence_async_smem();
         __syncthreads();
         const float* tp = reinterpret_cast<const float*>(&tile[0][0]);
-        if (warp == 0 && lane == 0) tile_store_issue(maps, tp, HAS_D ? tp + 3 * 1024 : nullptr, a.mask ? &mtile[0][0] : nullptr, tileX0, tileY0, b);
+        if (warp == 0 && lane == 0) tile_store_issue(maps, tp, (HAS_D || a.dep_o) ? tp + 3 * 1024 : nullptr, a.mask ? &mtile[0][0] : nullptr, tileX0, tileY0, b);
         if (a.coverage) {
             cnt = __reduce_add_sync(0xffffffffu, cnt);
             if (lane == 0 && cnt) atomicAdd(a.coverage + b, cnt);
