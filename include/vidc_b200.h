@@ -157,8 +157,9 @@ int vidc_build_homography(const vidc_camera *cam, const float *d_Ig, const float
 
 /* Layouts and speed (results never depend on them): contiguous NCHW planes whose width is a multiple of 32 and 16-byte aligned
    outputs (and mask) run the sheared kernels with the TMA write-out (bulk tensor stores, one output tensor map per call);
-   outputs a tensor map cannot describe take the same kernels' LSU write-out; everything else -- channels-last or otherwise
-   strided tensors, other widths -- is accepted without a copy by the strided kernels (about half the speed). */
+   outputs a tensor map cannot describe take the same kernels' LSU write-out; three-channel channels-last images (element
+   strides sc = 1, sw = 3, sh = 3 W, sn = 3 W H, input and output alike) have their own sheared kernels at about the planar speed;
+   everything else -- other strides, other widths -- is accepted without a copy by the strided kernels (about half the speed). */
 
 /* Replaces warp_with_gravity_center_aligned (:108-156): fused params + grid + grid_sample.
    x: (B,C,Hin,Win) any strides; y: (B,C,cam.H,cam.W).  d_H_out (B,3,3) may be NULL.

@@ -53,6 +53,13 @@ def main(cases=300, seed=2024):
         p = w.prepare(g, a)
         _, rgb_p, depth_p, mask_p = w.warp_rgbd(t(rgb), t(depth), params=p, depth_mode=mode)
         _, nhat_p = w.unwarp_normals(t(nrm), params=p)
+        if o.W % 32 == 0:                                          # channels-last kernels (kernels_shear_cl.cuh): the planar path's bits
+            xc = t(rgb).contiguous(memory_format=torch.channels_last); nc = t(nrm).contiguous(memory_format=torch.channels_last)
+            _, rgb_c, depth_c, mask_c = w.warp_rgbd(xc, t(depth), g, a, depth_mode=mode)
+            _, nhat_c = w.unwarp_normals(nc, g, a)
+            _, z_c = w.unwarp_normals(nc, params=p, normalize=False)
+            assert torch.equal(rgb_c, rgb_w) and torch.equal(depth_c, depth_w) and torch.equal(mask_c, mask), ("channels-last forward", case)
+            assert torch.equal(nhat_c, nhat) and torch.equal(z_c, z), ("channels-last inverse", case)
         with np.errstate(all="ignore"):
             _, oy = o.warp_with_gravity_center_aligned(rgb, I_g, I_a)
             _, oyd = o.warp_with_gravity_center_aligned(depth, I_g, I_a, interp_mode=mode)

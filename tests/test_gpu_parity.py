@@ -160,6 +160,45 @@ def test_channels_last_input_no_copy(cuda_device, oracle_mod):
     assert C.count_bit_mismatches(z.cpu().numpy(), oz) == 0
 
 
+@pytest.mark.parametrize("cam_name,kind", [("S1", "random"), ("S2", "random"), ("S3", "roll"), ("azure489", "random"), ("tiny", "edge")])
+def test_channels_last_fast_kernels(cuda_device, oracle_mod, cam_name, kind):
+    """torch.channels_last three-channel images (a CNN that runs in that memory format) take their own sheared kernels
+    (kernels_shear_cl.cuh: twelve loads off one address, a (96, 32) staging tile, one bulk tensor store): outputs come back
+    channels-last and carry the bits of the planar path -- fused calls, both depth modes, coverage, and the reference-shaped
+    methods; compile-time and run-time geometry, a canvas height that is not a multiple of the tile, extreme rolls."""
+    cam = C.CAMERAS.get(cam_name) or (404.0, 404.0, 319.529, 244.1902)           # 640 x 489, the real Azure Kinect canvas
+    from vi_depth_completion_b200.warping_2dof_alignment import Warping2DOFAlignment
+    w = Warping2DOFAlignment(*cam)
+    Hh, Ww = int(w.H), int(w.W)
+    B = 5
+    I_g, I_a = {"random": lambda: C.random_gravity(B, seed=99), "roll": lambda: C.extreme_roll_gravity(B, seed=4),
+                "edge": lambda: C.edge_case_gravity()}[kind]()
+    B = I_g.shape[0]
+    rgb, depth, normals = C.random_images(B, Hh, Ww, seed=23)
+    g, a = _t(I_g, cuda_device), _t(I_a, cuda_device)
+    x, d, n = _t(rgb, cuda_device), _t(depth, cuda_device), _t(normals, cuda_device)
+    xc, nc = x.contiguous(memory_format=torch.channels_last), n.contiguous(memory_format=torch.channels_last)
+    is_cl = lambda t: t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous()
+    for mode in ("bilinear", "nearest"):
+        H0, r0, d0, m0, c0 = w.warp_rgbd(x, d, g, a, depth_mode=mode, with_coverage=True)
+        H1, r1, d1, m1, c1 = w.warp_rgbd(xc, d, g, a, depth_mode=mode, with_coverage=True)
+        assert is_cl(r1) and torch.equal(r1, r0) and torch.equal(d1, d0) and torch.equal(m1, m0) and torch.equal(c1, c0) and torch.equal(H1, H0)
+    _, r2, _, m2 = w.warp_rgbd(xc, None, g, a)
+    assert is_cl(r2) and torch.equal(r2, r0) and torch.equal(m2, m0)
+    _, y0 = w.warp_with_gravity_center_aligned(x, g, a)
+    _, y1 = w.warp_with_gravity_center_aligned(xc, g, a)
+    assert is_cl(y1) and torch.equal(y1, y0)
+    for normalize in (True, False):
+        _, z0 = w.unwarp_normals(n, g, a, normalize=normalize)
+        _, z1 = w.unwarp_normals(nc, g, a, normalize=normalize)
+        assert is_cl(z1) and torch.equal(z1, z0)
+    _, z2 = w.inverse_warp_normal_image_with_gravity_center_aligned(nc, g, a)
+    assert is_cl(z2) and torch.equal(z2, z0)
+    p = w.prepare(g, a)
+    assert torch.equal(w.warp_rgbd(xc, d, params=p)[1], w.warp_rgbd(x, d, g, a)[1])
+    assert torch.equal(w.unwarp_normals(nc, params=p)[1], w.unwarp_normals(n, g, a)[1])
+
+
 def test_outputs_a_tensor_map_cannot_describe(cuda_device, oracle_mod):
     """The TMA write-out needs 16-byte aligned outputs (and mask): a caller of the C ABI that hands over anything else gets the
     LSU write-out of the same kernels -- same bits, no error.  Outputs placed 4 / 8 bytes into their allocations."""
